@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — joined rows/sec of the GPU hash join on BASELINE.json config 2 (and its N-GPU shuffled form).
+
+Workload (N = 1): "C2" = 2-table INNER hash join, 100 M build x 1 B probe rows, BIGINT key + 2 INT payloads per
+side, every probe row matches exactly once.  One step = build (consume + finish) + probe of the
+whole probe table.  value = probe rows / step time with inputs resident in HBM; e2e = the same join driven through
+the C-ABI with HOST (pinned) buffers, host<->device copies inside the timed region.
+
+N > 1 (weak scaling): every rank holds a 100 M x 1 B shard of an N-times larger join; both sides are hash-
+partitioned on the join key (ExecUtils.partition) and exchanged with one NCCL AllToAllv per column over NVLink,
+then joined locally — the plan shape of a hash/hash-distributed MPP join.  value = N x 1 B probe rows / max-over-
+ranks step time.
+
+`--impl reference` times the reference-shaped CPU path (oracle/, P = min(cores,16) driver threads, 1000-row chunks,
+shared CAS chained table) on a bounded sample of the same workload; rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C2_BUILD, C2_PROBE = 100_000_000, 1_000_000_000
+PROBE_ALG_BYTES = 68  # 16 probe row + 4 bucket head + 8 build key + 8 build payload + 32 output row
+BUILD_ALG_BYTES = 24  # 16 row read + 8 table write
+METRIC = "joined+aggregated rows/sec; achieved HBM GB/s vs peak, at 1/2/4/8 B200"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("GSQL_BENCH_SCALE", "1.0")),
+                    help="fraction of config 2 (testing only; the contract value is 1.0)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-batch", type=int, default=125_000_000, help="probe rows per host batch in the e2e leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def host_threads() -> int:
+    return max(1, min(os.cpu_count() or 1, 16))  # ExecUtils.getParallelismForLocal: min(cores, 16)
+
+
+def cpu_sample(build_rows: int, probe_rows: int, repeats: int = 1):
+    """Reference-shaped CPU join (oracle) on a bounded sample; returns (rows/s incl. build, detail dict)."""
+    from galaxysql_b200 import synth
+    from oracle import oracle as orc
+    P = host_threads()
+    build, probe = synth.c2_tables_np(build_rows, probe_rows)
+    spec = orc.JoinSpec(orc.JOIN_INNER, [0], [0], [orc.T_INT64])
+    best = None
+    for _ in range(repeats):
+        r = orc.mt_join(spec, [(c, None) for c in probe], [(c, None) for c in build], nthreads=P, chunk_rows=1000)
+        assert r["out_rows"] == probe_rows
+        t = r["build_s"] + r["probe_s"]
+        if best is None or t < best[0]:
+            best = (t, r)
+    t, r = best
+    return probe_rows / t, {"build_s": r["build_s"], "probe_s": r["probe_s"], "threads": P}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sb, sp = 2_000_000, 20_000_000  # 1/50 of config 2 per step: a few seconds of CPU work on 8-16 cores
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, d = cpu_sample(sb, sp)
+        if i >= args.warmup:
+            times.append(sp / v)
+    ms = 1000.0 * sum(times) / len(times)
+    value = sp / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "C2 inner hash join, BIGINT key + 2 INT payloads (CPU sample)", "build_rows": sb, "probe_rows": sp,
+                   "note": "reference Java cannot run (no JDK); oracle port in the reference's parallel shape"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": host_threads(), "kind": "port",
+                         "sample": f"{sb} build x {sp} probe rows per step, {host_threads()} threads, 1000-row chunks"},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from galaxysql_b200 import api, native as N, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = api.Context(local_rank)
+    stream = ctx.torch_stream()
+
+    nb = int(C2_BUILD * args.scale)
+    npr = int(C2_PROBE * args.scale)
+    key_space = nb * world
+    # ---- synthetic shard on the device
+    g = torch.Generator(device=dev)
+    g.manual_seed(42)
+    if world == 1:
+        perm = torch.randperm(nb, generator=g, device=dev, dtype=torch.int64)
+    else:  # rank r holds keys {r, r+W, r+2W, ...} of the global permutation space, shuffled
+        g.manual_seed(42 + rank)
+        perm = torch.randperm(nb, generator=g, device=dev, dtype=torch.int64) * world + rank
+    build, probe = synth.c2_tables_t(nb, npr, dev, key_space=key_space, probe_start=rank * npr, build_perm=perm)
+    torch.cuda.synchronize()
+
+    types = [N.T_INT64, N.T_INT32, N.T_INT32]
+    out_types = types + types
+    tt = {N.T_INT64: torch.int64, N.T_INT32: torch.int32}
+    cap = npr if world == 1 else int(npr * 1.02) + 1_000_000
+    out_cols = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in out_types]
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.tensor(list(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        api.comm_init(ctx, world, rank, bytes(uid.cpu().tolist()))
+        xb = api.Exchange(ctx, types, [0], world)
+        xp = api.Exchange(ctx, types, [0], world)
+        bcap = int(nb * 1.05) + 1_000_000
+        rb = [(torch.empty(bcap, dtype=tt[t], device=dev), None) for t in types]
+        rp = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in types]
+
+    def b(cols):
+        return [(c, None) for c in cols]
+
+    state = {"out_rows": 0, "info": None}
+
+    def step():
+        if world > 1:
+            nbr, _ = xb.all_to_all_into(b(build), rb, bcap)
+            npr_r, _ = xp.all_to_all_into(b(probe), rp, cap)
+            bcols = [(c[:nbr], None) for c, _ in rb]
+            pcols = [(c[:npr_r], None) for c, _ in rp]
+        else:
+            bcols, pcols = b(build), b(probe)
+        j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=len(bcols[0][0]))
+        j.build_consume(bcols)
+        j.build_finish()
+        state["out_rows"] = j.probe_into(pcols, out_cols, cap)
+        state["info"] = j.info()
+        j.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile(True)
+    ctx.profile_reset()
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        rows_t = torch.tensor([state["out_rows"]], dtype=torch.int64, device=dev)
+        dist.all_reduce(rows_t)
+        total_out = int(rows_t.item())
+    else:
+        total_out = state["out_rows"]
+    assert total_out == npr * world, (total_out, npr * world)  # every probe row matches exactly once
+    ms_step = ms_total / args.steps
+    value = npr * world / (ms_step / 1000.0)
+
+    # ---- spot-check the last step's output on the device (parity proper lives in tests/)
+    n_out = state["out_rows"]
+    chk = min(n_out, 1 << 22)
+    assert bool((out_cols[0][0][:chk] == out_cols[3][0][:chk]).all()), "probe.key != build.key in the output"
+
+    # ---- roofline of the dominant kernel(s): the probe phase
+    probe_kernels = [k for k in prof if k.startswith("join_probe") or k.startswith("join_scan")]
+    probe_ms = sum(prof[k][1] for k in probe_kernels) / args.steps
+    probe_rows_rank = n_out
+    peak, peak_src = measured_peak_gbs()
+    achieved = PROBE_ALG_BYTES * probe_rows_rank / (probe_ms / 1000.0) / 1e9 if probe_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "+".join(sorted(probe_kernels)), "kernel_ms_per_step": probe_ms,
+                "algorithmic_bytes_per_probe_row": PROBE_ALG_BYTES, "peak_source": peak_src,
+                "per_kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())}}
+
+    # ---- e2e: host (pinned) buffers through the C-ABI, rank-local, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev)
+    # free the big device tables before the CPU leg
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sb, sp = 1_000_000, 10_000_000
+        v, d = cpu_sample(sb, sp)
+        cpu = {"value": v, "unit": "rows/s", "cores": d["threads"], "kind": "port",
+               "sample": f"1/100 of config 2: {sb} build x {sp} probe rows, {d['threads']} threads, 1000-row chunks "
+                         f"(build {d['build_s']:.2f}s + probe {d['probe_s']:.2f}s)"}
+    if rank == 0:
+        info = state["info"]
+        line = {
+            "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+            "data": "synthetic",
+            "config": {"workload": "C2: inner hash join 100M build x 1B probe, BIGINT key + 2 INT payloads" +
+                                   (f" per GPU, hash-shuffled across {world} GPUs (AllToAllv)" if world > 1 else ", 1 GPU"),
+                       "build_rows_per_gpu": nb, "probe_rows_per_gpu": npr, "scale": args.scale,
+                       "l2": "inputs (16 GB probe per step) are far larger than the 126 MB L2; no explicit flush",
+                       "step": "build (consume + finish) + probe of the full probe table" + (" after the key shuffle" if world > 1 else ""),
+                       "table_slots": int(info.table_slots), "fast_path": int(info.fast_path), "partitions": int(info.partitions)},
+            "roofline": roofline,
+            "clocks": clocks,
+            "gpu_launches": int(launches),
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        ctx.lib.gsql_comm_destroy(ctx.ptr)
+        dist.destroy_process_group()
+
+
+def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
+    """The join as a host caller drives it: pinned host Blocks in, pinned host Blocks out, every copy timed."""
+    import torch
+    import torch.distributed as dist
+    batch = min(args.e2e_batch, npr)
+    types = [N.T_INT64, N.T_INT32, N.T_INT32]
+    tt = {N.T_INT64: torch.int64, N.T_INT32: torch.int32}
+    # host copies of the inputs (pinned) — made once, outside the timed region, like a caller that owns them
+    hbuild = [torch.empty(nb, dtype=c.dtype, pin_memory=True) for c in build]
+    for h, c in zip(hbuild, build):
+        h.copy_(c)
+    hprobe = [torch.empty(npr, dtype=c.dtype, pin_memory=True) for c in probe]
+    for h, c in zip(hprobe, probe):
+        h.copy_(c)
+    hout = [torch.empty(batch, dtype=tt[t], pin_memory=True) for t in types + types]
+    torch.cuda.synchronize()
+
+    def view(tensors, lo, hi):
+        return [(t[lo:hi].numpy(), None) for t in tensors]
+
+    def step():
+        j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nb)
+        j.build_consume(view(hbuild, 0, nb))
+        j.build_finish()
+        total = 0
+        for lo in range(0, npr, batch):
+            hi = min(npr, lo + batch)
+            total += j.probe_into(view(hprobe, lo, hi), [(t.numpy(), None) for t in hout], batch)
+        j.close()
+        return total
+
+    steps = max(1, min(args.steps, 3))
+    step()  # warm-up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        total = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    assert total == npr
+    h2d = nb * 16 + npr * 16
+    d2h = npr * 32
+    return {"value": npr * world / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": dt * 1000.0, "steps": steps, "probe_batch_rows": batch,
+            "path": "gsql_join_build_consume/gsql_join_probe with GSQL_MEM_HOST pinned batches" +
+                    (" (rank-local shard, no shuffle)" if world > 1 else "")}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,648 @@
+// agg.cu — GPU hash aggregation behind gsql_agg_* (drop-in for HashAggExec consume / buildConsume / nextChunk).
+//
+// Reference path replaced (EX/ = polardbx-executor/src/main/java/com/alibaba/polardbx/executor/):
+//   EX/operator/HashAggExec.java:133-145 (consumeChunk), :158-162 (buildConsume)
+//   EX/operator/util/AggOpenHashMap.java:100-139 (putChunk), :160-194 (buildChunks)
+//   EX/operator/util/GroupOpenHashMap.java:142-187 (doInnerPutArray, rehash)
+//   EX/calc/aggfunctions/{CountRow,Count,LittleNum2DoubleSum,SpecificType2DoubleAvgV2,LittleNum2DecimalSum,
+//                         Long2LongSum0,Int2IntMax,...}.java (accumulate / writeResultTo)
+//
+// B200 layout: one open-addressing table of 16-byte slots {digest, dense group id} in HBM (load <= 0.5); group
+// keys and every accumulator are columnar arrays indexed by group id, updated with native L2 atomics
+// (int64 add, fp64 add, int64 min/max on an order-preserving transform).  SUM(int|bigint) is exact 128-bit
+// (lo/hi with carry), which equals the reference's long-with-overflow-escape-to-DECIMAL result.
+// Two specialisations sit in front of the generic kernel (agg_fast.cuh): a shared-memory privatised table for
+// low-cardinality group-bys and a key-in-slot table for single-integer-key high-cardinality group-bys.
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned long long DIGEST_EMPTY = 0x8000000000000000ULL;
+constexpr int GID_PENDING = -1;
+enum { C_NGROUPS = 0, C_OVERFLOW = 1, C_COUNT = 4 };
+
+struct __align__(16) ASlot {
+    unsigned long long digest;
+    int gid;
+    int pad;
+};
+
+struct AggDev {  // device view of one aggregator's state
+    int32_t kind, in_type, ncols, filter_col;
+    int32_t cols[4];
+    int64_t *l;      // count | int64 sum0 | min/max (sortable) | SUM(int) low word
+    int64_t *hi;     // SUM(int) high word
+    double *d;       // fp64 sum
+    uint8_t *has;    // "state is not NULL"
+};
+
+struct AggParams {
+    DColSet in;
+    KeySet keys;
+    int32_t nkeys, naggs, exact, pad;
+    ASlot *slots;
+    uint64_t nslots;
+    int64_t *gkey[GSQL_MAX_KEYS];  // group keys by gid (int widened / canonical double bits)
+    uint8_t *gnull[GSQL_MAX_KEYS];
+    AggDev agg[GSQL_MAX_AGGS];
+    unsigned long long *counters;  // [C_NGROUPS], [C_OVERFLOW]
+    int64_t *overflow_rows;        // row indices that found the table full
+    const int64_t *row_list;       // non-null: process these rows (overflow re-run) instead of [row0, row0+rows)
+    int64_t row0, rows;
+    int64_t gcap;                  // groups the arrays can hold before a grow (a slack margin sits above it)
+};
+
+// canonical 8-byte image of a key component; NULL has its own flag
+__device__ __forceinline__ int64_t canon_key(const KeyVal &k, int utype) {
+    if (k.is_null) return 0;
+    if (utype == GSQL_T_FP64) {
+        double v = __longlong_as_double(k.i);
+        if (v != v) return 0x7ff8000000000000LL;
+        if (v == 0.0) return 0;
+    }
+    return k.i;
+}
+
+// order-preserving map double -> int64 (so that atomicMin/atomicMax on int64 implement Math.min/Math.max incl.
+// -0.0 < +0.0).  NaN must win both: it is mapped to the extreme of the respective direction.
+__device__ __forceinline__ long long dbl_sortable(double v, bool for_max) {
+    if (v != v) return for_max ? 0x7fffffffffffffffLL : (long long)0x8000000000000000ULL;
+    long long b = __double_as_longlong(v);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__host__ __device__ __forceinline__ double dbl_unsortable(long long s, bool for_max) {
+    if (for_max && s == 0x7fffffffffffffffLL) return __builtin_nan("");
+    if (!for_max && s == (long long)0x8000000000000000ULL) return __builtin_nan("");
+    long long b = s ^ ((s >> 63) & 0x7fffffffffffffffLL);
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+__device__ __forceinline__ bool in_null(const DCol &c, int64_t r) { return c.nulls != nullptr && c.nulls[r] != 0; }
+
+// Finds or creates the group of input row r.  Returns gid >= 0, or -1 when the table is full (row -> overflow).
+__device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
+    if (P.nkeys == 0) return 0;
+    int64_t kv[GSQL_MAX_KEYS];
+    bool kn[GSQL_MAX_KEYS];
+    unsigned long long d;
+    uint64_t s;
+    bool dedicated = false;
+    if (P.exact) {
+        KeyVal k = gsql_load_key(P.keys.c[0], r, P.keys.utype[0]);
+        kn[0] = k.is_null;
+        kv[0] = canon_key(k, P.keys.utype[0]);
+        d = (unsigned long long)kv[0];
+        if (k.is_null) { s = P.nslots + 1; dedicated = true; }          // NULL group key is an ordinary key (Block.java:136-145)
+        else if (d == DIGEST_EMPTY) { s = P.nslots; dedicated = true; }
+    } else {
+        unsigned long long h = 0x243F6A8885A308D3ULL;
+#pragma unroll 1
+        for (int c = 0; c < P.nkeys; c++) {
+            KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
+            kn[c] = k.is_null;
+            kv[c] = canon_key(k, P.keys.utype[c]);
+            h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (k.is_null ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+        }
+        if (h == DIGEST_EMPTY) h ^= 1;
+        d = h;
+    }
+    if (!dedicated) s = __umul64hi(gsql_fmix64(d), P.nslots);
+    while (true) {
+        ASlot *sl = &P.slots[s];
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sl->digest);
+        bool mine = false;
+        if (dedicated) {
+            // dedicated slots are claimed through gid only: digest field carries a "claimed" mark
+            unsigned long long prev = cur == DIGEST_EMPTY ? atomicCAS(&sl->digest, DIGEST_EMPTY, 1ULL) : cur;
+            if (prev == DIGEST_EMPTY) mine = true;
+        } else if (cur == DIGEST_EMPTY) {
+            if (*reinterpret_cast<volatile unsigned long long *>(&P.counters[C_NGROUPS]) >= (unsigned long long)P.gcap) return -1;
+            unsigned long long prev = atomicCAS(&sl->digest, DIGEST_EMPTY, d);
+            if (prev == DIGEST_EMPTY) mine = true;
+            else cur = prev;
+        }
+        if (mine) {  // first appearance: allocate the dense group id, publish keys, then the id
+            int gid = (int)atomicAdd(&P.counters[C_NGROUPS], 1ULL);
+            for (int c = 0; c < P.nkeys; c++) {
+                P.gkey[c][gid] = kv[c];
+                P.gnull[c][gid] = kn[c] ? 1 : 0;
+            }
+            __threadfence();
+            *reinterpret_cast<volatile int *>(&sl->gid) = gid;
+            return gid;
+        }
+        if (dedicated || cur == d) {
+            int gid;
+            while ((gid = *reinterpret_cast<volatile int *>(&sl->gid)) == GID_PENDING) __nanosleep(20);
+            if (P.exact) return gid;
+            __threadfence();
+            bool eq = true;
+            for (int c = 0; c < P.nkeys && eq; c++) {
+                bool gn = *reinterpret_cast<volatile uint8_t *>(&P.gnull[c][gid]) != 0;
+                long long gv = *reinterpret_cast<volatile long long *>(&P.gkey[c][gid]);
+                if (gn != kn[c] || (!gn && gv != kv[c])) eq = false;
+            }
+            if (eq) return gid;
+        }
+        if (++s == P.nslots) s = 0;
+    }
+}
+
+__device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {
+    if (c.type == GSQL_T_INT32) return reinterpret_cast<const int32_t *>(c.data)[r];
+    if (c.type == GSQL_T_INT64) return reinterpret_cast<const int64_t *>(c.data)[r];
+    return (int64_t) reinterpret_cast<const double *>(c.data)[r];
+}
+__device__ __forceinline__ double in_f64(const DCol &c, int64_t r) {
+    if (c.type == GSQL_T_FP64) return reinterpret_cast<const double *>(c.data)[r];
+    if (c.type == GSQL_T_INT64) return (double)reinterpret_cast<const int64_t *>(c.data)[r];
+    return (double)reinterpret_cast<const int32_t *>(c.data)[r];
+}
+
+__device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, int gid, int64_t r) {
+    if (a.filter_col >= 0) {  // AggOpenHashMap.java:114-131 — only Boolean / Long objects filter
+        const DCol &f = P.in.c[a.filter_col];
+        if (f.type == GSQL_T_INT64 && !in_null(f, r) && reinterpret_cast<const int64_t *>(f.data)[r] < 1) return;
+    }
+    switch (a.kind) {
+    case GSQL_AGG_COUNT_STAR:
+        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
+        return;
+    case GSQL_AGG_COUNT:
+        for (int i = 0; i < a.ncols; i++)
+            if (in_null(P.in.c[a.cols[i]], r)) return;
+        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
+        return;
+    default: break;
+    }
+    const DCol &c = P.in.c[a.cols[0]];
+    if (in_null(c, r)) return;
+    switch (a.kind) {
+    case GSQL_AGG_SUM:
+        if (a.in_type == GSQL_T_FP64) {
+            atomicAdd(&a.d[gid], in_f64(c, r));
+        } else {  // exact 128-bit: lo += v (carry out), hi += sign extension + carry
+            long long v = in_i64(c, r);
+            unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)v);
+            unsigned long long sum = old + (unsigned long long)v;
+            long long carry = (sum < old ? 1 : 0) + (v < 0 ? -1 : 0);
+            if (carry) atomicAdd(reinterpret_cast<unsigned long long *>(&a.hi[gid]), (unsigned long long)carry);
+        }
+        a.has[gid] = 1;
+        return;
+    case GSQL_AGG_AVG:
+        atomicAdd(&a.d[gid], in_f64(c, r));
+        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
+        a.has[gid] = 1;
+        return;
+    case GSQL_AGG_SUM0:
+        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)in_i64(c, r));
+        return;
+    case GSQL_AGG_MIN:
+    case GSQL_AGG_MAX: {
+        bool mx = a.kind == GSQL_AGG_MAX;
+        long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(in_f64(c, r), mx) : in_i64(c, r);
+        if (mx) atomicMax(reinterpret_cast<long long *>(&a.l[gid]), v);
+        else atomicMin(reinterpret_cast<long long *>(&a.l[gid]), v);
+        a.has[gid] = 1;
+        return;
+    }
+    default: return;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ AggParams P) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.rows; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = P.row_list ? P.row_list[i] : P.row0 + i;
+        int gid = find_group(P, r);
+        if (gid < 0) {
+            unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
+            P.overflow_rows[o] = r;
+            continue;
+        }
+        for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_aslots_init(ASlot *slots, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        int4 v;
+        v.x = 0;
+        v.y = (int)0x80000000;
+        v.z = GID_PENDING;
+        v.w = 0;
+        reinterpret_cast<int4 *>(slots)[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fill_i64(int64_t *p, int64_t v, int64_t from, int64_t to) {
+    for (int64_t i = from + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < to; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// re-insert groups [0, ngroups) into a fresh slot array after a grow (GroupOpenHashMap.rehash:171-187)
+__global__ void __launch_bounds__(256) k_agg_rehash(const __grid_constant__ AggParams P, int64_t ngroups) {
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long d;
+        uint64_t s;
+        bool dedicated = false;
+        if (P.exact) {
+            d = (unsigned long long)P.gkey[0][g];
+            if (P.gnull[0][g]) { s = P.nslots + 1; dedicated = true; }
+            else if (d == DIGEST_EMPTY) { s = P.nslots; dedicated = true; }
+        } else {
+            unsigned long long h = 0x243F6A8885A308D3ULL;
+            for (int c = 0; c < P.nkeys; c++) {
+                bool n = P.gnull[c][g] != 0;
+                h = gsql_fmix64(h ^ (unsigned long long)P.gkey[c][g]) + (n ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+            }
+            if (h == DIGEST_EMPTY) h ^= 1;
+            d = h;
+        }
+        if (dedicated) {
+            P.slots[s].digest = 1ULL;
+            P.slots[s].gid = (int)g;
+            continue;
+        }
+        s = __umul64hi(gsql_fmix64(d), P.nslots);
+        while (atomicCAS(&P.slots[s].digest, DIGEST_EMPTY, d) != DIGEST_EMPTY)
+            if (++s == P.nslots) s = 0;
+        P.slots[s].gid = (int)g;
+    }
+}
+
+struct FinalCol {
+    void *data;
+    uint8_t *nulls;
+    int32_t type, pad;
+};
+struct FinalParams {
+    int32_t nkeys, naggs;
+    int64_t ngroups;
+    const int64_t *gkey[GSQL_MAX_KEYS];
+    const uint8_t *gnull[GSQL_MAX_KEYS];
+    int32_t key_types[GSQL_MAX_KEYS];
+    AggDev agg[GSQL_MAX_AGGS];
+    FinalCol out[GSQL_MAX_COLS];
+};
+
+// writeResultTo per group, in group-id order (AggOpenHashMap.buildValueChunks:160-178)
+__global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ FinalParams F) {
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < F.ngroups; g += (int64_t)gridDim.x * blockDim.x) {
+        int col = 0;
+        for (int c = 0; c < F.nkeys; c++, col++) {
+            const FinalCol &o = F.out[col];
+            bool n = F.gnull[c][g] != 0;
+            o.nulls[g] = n ? 1 : 0;
+            int64_t v = n ? 0 : F.gkey[c][g];
+            if (o.type == GSQL_T_INT32) reinterpret_cast<int32_t *>(o.data)[g] = (int32_t)v;
+            else reinterpret_cast<int64_t *>(o.data)[g] = v;  // INT64, or FP64 bits
+        }
+        for (int a = 0; a < F.naggs; a++, col++) {
+            const FinalCol &o = F.out[col];
+            const AggDev &ag = F.agg[a];
+            switch (ag.kind) {
+            case GSQL_AGG_COUNT_STAR: case GSQL_AGG_COUNT: case GSQL_AGG_SUM0:
+                o.nulls[g] = 0;
+                reinterpret_cast<int64_t *>(o.data)[g] = ag.l[g];
+                break;
+            case GSQL_AGG_SUM:
+                o.nulls[g] = ag.has[g] ? 0 : 1;
+                if (ag.in_type == GSQL_T_FP64) reinterpret_cast<double *>(o.data)[g] = ag.has[g] ? ag.d[g] : 0.0;
+                else {
+                    reinterpret_cast<int64_t *>(o.data)[2 * g] = ag.has[g] ? ag.l[g] : 0;
+                    reinterpret_cast<int64_t *>(o.data)[2 * g + 1] = ag.has[g] ? ag.hi[g] : 0;
+                }
+                break;
+            case GSQL_AGG_AVG: {  // sum / (double) count; NULL when no value (SpecificType2DoubleAvgV2.java:70-84)
+                bool ok = ag.has[g] && ag.l[g] != 0;
+                o.nulls[g] = ok ? 0 : 1;
+                reinterpret_cast<double *>(o.data)[g] = ok ? ag.d[g] / (double)ag.l[g] : 0.0;
+                break;
+            }
+            default: {  // MIN / MAX
+                bool has = ag.has[g] != 0;
+                o.nulls[g] = has ? 0 : 1;
+                if (ag.in_type == GSQL_T_FP64) reinterpret_cast<double *>(o.data)[g] = has ? dbl_unsortable(ag.l[g], ag.kind == GSQL_AGG_MAX) : 0.0;
+                else if (ag.in_type == GSQL_T_INT32) reinterpret_cast<int32_t *>(o.data)[g] = has ? (int32_t)ag.l[g] : 0;
+                else reinterpret_cast<int64_t *>(o.data)[g] = has ? ag.l[g] : 0;
+            }
+            }
+        }
+    }
+}
+
+int grid_rows(gsql_ctx *ctx, int64_t rows, int block, int per_sm) {
+    int64_t g = div_up(rows, block);
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int agg_out_type(int kind, int in_type) {
+    switch (kind) {
+    case GSQL_AGG_COUNT_STAR: case GSQL_AGG_COUNT: case GSQL_AGG_SUM0: return GSQL_T_INT64;
+    case GSQL_AGG_SUM: return in_type == GSQL_T_FP64 ? GSQL_T_FP64 : GSQL_T_DEC128;
+    case GSQL_AGG_AVG: return GSQL_T_FP64;
+    default: return in_type;
+    }
+}
+
+}  // namespace
+
+#include "agg_fast.cuh"
+
+struct gsql_agg {
+    gsql_ctx *ctx;
+    gsql_agg_spec spec;
+    int32_t nkeys = 0, naggs = 0;
+    int32_t in_type[GSQL_MAX_AGGS];
+    int32_t nout = 0;
+    int32_t out_types[GSQL_MAX_COLS];
+    // table + state
+    DevBuf slots, counters, overflow;
+    uint64_t nslots = 0;
+    int64_t gcap = 0, garr = 0;  // grow threshold, array capacity (gcap + slack)
+    int64_t slack = 0;
+    DevBuf gkey[GSQL_MAX_KEYS], gnull[GSQL_MAX_KEYS];
+    DevBuf sl[GSQL_MAX_AGGS], shi[GSQL_MAX_AGGS], sd[GSQL_MAX_AGGS], shas[GSQL_MAX_AGGS];
+    int64_t ngroups = 0;
+    bool finished = false;
+    DevBuf out_data[GSQL_MAX_COLS], out_nulls[GSQL_MAX_COLS];
+    int64_t cursor = 0;
+    AggFast fast;
+};
+
+static int64_t init_value(int kind) {
+    if (kind == GSQL_AGG_MIN) return 0x7fffffffffffffffLL;
+    if (kind == GSQL_AGG_MAX) return (int64_t)0x8000000000000000ULL;
+    return 0;
+}
+
+// (Re)allocates slots and state arrays for `gcap` groups, keeping the first `keep` groups' keys and states.
+static gsql_status agg_resize(gsql_agg *a, int64_t gcap, int64_t keep) {
+    gsql_ctx *ctx = a->ctx;
+    int64_t garr = gcap + a->slack;
+    uint64_t nslots = (uint64_t)(2 * garr);
+    DevBuf nslot;
+    GSQL_TRY(nslot.alloc(ctx, (size_t)(nslots + 2) * sizeof(ASlot)));
+    {
+        KernelScope ks(ctx, "agg_slots_init");
+        k_aslots_init<<<grid_rows(ctx, (int64_t)nslots + 2, 256, 8), 256, 0, ctx->stream>>>(nslot.as<ASlot>(), nslots + 2);
+    }
+    a->slots.release();
+    a->slots.ctx = ctx;
+    a->slots.p = nslot.p;
+    a->slots.bytes = nslot.bytes;
+    nslot.p = nullptr;
+    a->nslots = nslots;
+    for (int k = 0; k < a->nkeys; k++) {
+        GSQL_TRY(a->gkey[k].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
+        GSQL_TRY(a->gnull[k].grow(ctx, (size_t)garr, (size_t)keep));
+    }
+    for (int i = 0; i < a->naggs; i++) {
+        int kind = a->spec.aggs[i].kind;
+        GSQL_TRY(a->sl[i].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
+        {
+            KernelScope ks(ctx, "agg_state_init");
+            k_fill_i64<<<grid_rows(ctx, garr - keep, 256, 8), 256, 0, ctx->stream>>>(a->sl[i].as<int64_t>(), init_value(kind), keep, garr);
+        }
+        GSQL_TRY(a->shas[i].grow(ctx, (size_t)garr, (size_t)keep));
+        GSQL_CUDA(ctx, cudaMemsetAsync((char *)a->shas[i].p + keep, 0, (size_t)(garr - keep), ctx->stream));
+        if (kind == GSQL_AGG_SUM && a->in_type[i] != GSQL_T_FP64) {
+            GSQL_TRY(a->shi[i].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
+            GSQL_CUDA(ctx, cudaMemsetAsync((char *)a->shi[i].p + keep * 8, 0, (size_t)(garr - keep) * 8, ctx->stream));
+        }
+        if ((kind == GSQL_AGG_SUM && a->in_type[i] == GSQL_T_FP64) || kind == GSQL_AGG_AVG) {
+            GSQL_TRY(a->sd[i].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
+            GSQL_CUDA(ctx, cudaMemsetAsync((char *)a->sd[i].p + keep * 8, 0, (size_t)(garr - keep) * 8, ctx->stream));
+        }
+    }
+    a->gcap = gcap;
+    a->garr = garr;
+    return GSQL_OK;
+}
+
+static void agg_fill_params(gsql_agg *a, const StagedBatch *sb, AggParams *P) {
+    memset(P, 0, sizeof(*P));
+    if (sb) {
+        P->in.n = sb->ncols;
+        for (int i = 0; i < sb->ncols; i++) P->in.c[i] = sb->cols[i];
+        P->keys.n = a->nkeys;
+        for (int k = 0; k < a->nkeys; k++) {
+            P->keys.c[k] = sb->cols[a->spec.groups[k]];
+            P->keys.utype[k] = a->spec.input_types[a->spec.groups[k]];
+        }
+    }
+    P->nkeys = a->nkeys;
+    P->naggs = a->naggs;
+    P->exact = a->nkeys == 1;
+    P->slots = a->slots.as<ASlot>();
+    P->nslots = a->nslots;
+    for (int k = 0; k < a->nkeys; k++) {
+        P->gkey[k] = a->gkey[k].as<int64_t>();
+        P->gnull[k] = a->gnull[k].as<uint8_t>();
+    }
+    for (int i = 0; i < a->naggs; i++) {
+        AggDev &d = P->agg[i];
+        const gsql_agg_call &c = a->spec.aggs[i];
+        d.kind = c.kind;
+        d.in_type = a->in_type[i];
+        d.ncols = c.ncols;
+        d.filter_col = c.filter_arg;
+        for (int q = 0; q < 4; q++) d.cols[q] = c.cols[q];
+        d.l = a->sl[i].as<int64_t>();
+        d.hi = a->shi[i].as<int64_t>();
+        d.d = a->sd[i].as<double>();
+        d.has = a->shas[i].as<uint8_t>();
+    }
+    P->counters = a->counters.as<unsigned long long>();
+    P->overflow_rows = a->overflow.as<int64_t>();
+    P->gcap = a->gcap;
+}
+
+extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec, gsql_agg **out) {
+    if (!ctx || !spec || !out) return GSQL_E_INVALID;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    *out = nullptr;
+    const gsql_agg_spec &s = *spec;
+    if (s.n_input_cols < 0 || s.n_input_cols > GSQL_MAX_COLS || s.ngroups < 0 || s.ngroups > GSQL_MAX_KEYS || s.naggs < 0 || s.naggs > GSQL_MAX_AGGS)
+        return gsql_set_error(ctx, GSQL_E_INVALID, "bad agg spec sizes");
+    if (s.ngroups + s.naggs > GSQL_MAX_COLS) return gsql_set_error(ctx, GSQL_E_INVALID, "too many output columns");
+    for (int i = 0; i < s.n_input_cols; i++)
+        if (s.input_types[i] < GSQL_T_INT32 || s.input_types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "input col %d type", i);
+    for (int k = 0; k < s.ngroups; k++)
+        if (s.groups[k] < 0 || s.groups[k] >= s.n_input_cols) return gsql_set_error(ctx, GSQL_E_INVALID, "group col out of range");
+    gsql_agg *a = new gsql_agg();
+    a->ctx = ctx;
+    a->spec = s;
+    a->nkeys = s.ngroups;
+    a->naggs = s.naggs;
+    for (int k = 0; k < s.ngroups; k++) a->out_types[a->nout++] = s.input_types[s.groups[k]];
+    for (int i = 0; i < s.naggs; i++) {
+        const gsql_agg_call &c = s.aggs[i];
+        if (c.kind < GSQL_AGG_COUNT_STAR || c.kind > GSQL_AGG_SUM0) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "agg kind %d", c.kind); }
+        int need = c.kind == GSQL_AGG_COUNT_STAR ? 0 : 1;
+        if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != 1)) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
+        for (int q = 0; q < c.ncols; q++)
+            if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
+        if (c.filter_arg >= s.n_input_cols) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: filter column", i); }
+        a->in_type[i] = c.ncols > 0 ? s.input_types[c.cols[0]] : GSQL_T_INT64;
+        // planner-time fall-through cases (the stock HashAggExec keeps them): AVG over integers is DECIMAL division
+        if (c.kind == GSQL_AGG_AVG && a->in_type[i] != GSQL_T_FP64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG(integer) -> DECIMAL not on the GPU path"); }
+        if (c.kind == GSQL_AGG_SUM0 && a->in_type[i] != GSQL_T_INT64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "SUM0 needs BIGINT input"); }
+        a->out_types[a->nout++] = agg_out_type(c.kind, a->in_type[i]);
+    }
+    cudaSetDevice(ctx->device);
+    a->slack = (int64_t)ctx->sm_count * 2048 + 1024;
+    int64_t gcap = s.expected_groups > 0 ? s.expected_groups : 1024;
+    if (gcap < 65536) gcap = 65536;
+    gsql_status st = a->counters.alloc(ctx, C_COUNT * 8);
+    if (st == GSQL_OK) st = (cudaMemsetAsync(a->counters.p, 0, C_COUNT * 8, ctx->stream) == cudaSuccess) ? GSQL_OK : GSQL_E_CUDA;
+    if (st == GSQL_OK) st = agg_resize(a, gcap, 0);
+    if (st == GSQL_OK && a->nkeys == 0) {  // noGroupBy: one group exists from the start (AggOpenHashMap.java:93-96)
+        unsigned long long one = 1;
+        cudaMemcpyAsync(a->counters.p, &one, 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        a->ngroups = 1;
+    }
+    if (st != GSQL_OK) { delete a; return st; }
+    *out = a;
+    return GSQL_OK;
+}
+
+extern "C" void gsql_agg_destroy(gsql_agg *a) {
+    if (!a) return;
+    cudaSetDevice(a->ctx->device);
+    delete a;
+}
+
+static gsql_status agg_read_counters(gsql_agg *a, unsigned long long *h) {
+    gsql_ctx *ctx = a->ctx;
+    GSQL_CUDA(ctx, cudaMemcpyAsync(h, a->counters.p, C_COUNT * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
+    if (!a) return GSQL_E_INVALID;
+    gsql_ctx *ctx = a->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (a->finished) return gsql_set_error(ctx, GSQL_E_STATE, "consume after finish");
+    GSQL_TRY(validate_batch(ctx, batch, a->spec.n_input_cols, a->spec.input_types));
+    if (batch->rows == 0) return GSQL_OK;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    StagedBatch sb;
+    GSQL_TRY(stage_batch(ctx, batch, &sb));
+    GSQL_TRY(a->overflow.grow(ctx, (size_t)batch->rows * 8, 0));
+    AggParams P;
+    agg_fill_params(a, &sb, &P);
+    P.row0 = 0;
+    P.rows = batch->rows;
+    P.row_list = nullptr;
+    DevBuf pending;  // overflow rows being re-run
+    while (true) {
+        {
+            KernelScope ks(ctx, "agg_consume");
+            k_agg_consume<<<grid_rows(ctx, P.rows, 256, 8), 256, 0, ctx->stream>>>(P);
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+        unsigned long long h[C_COUNT];
+        GSQL_TRY(agg_read_counters(a, h));
+        a->ngroups = (int64_t)h[C_NGROUPS];
+        int64_t nover = (int64_t)h[C_OVERFLOW];
+        if (nover == 0) break;
+        // table full: double (at least) the group capacity, re-insert the groups, re-run only the overflowed rows
+        GSQL_TRY(pending.alloc(ctx, (size_t)nover * 8));
+        GSQL_CUDA(ctx, cudaMemcpyAsync(pending.p, a->overflow.p, (size_t)nover * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        unsigned long long zero = 0;
+        GSQL_CUDA(ctx, cudaMemcpyAsync(a->counters.as<unsigned long long>() + C_OVERFLOW, &zero, 8, cudaMemcpyHostToDevice, ctx->stream));
+        int64_t ncap = a->gcap * 2;
+        while (ncap < a->ngroups + nover / 4) ncap *= 2;
+        GSQL_TRY(agg_resize(a, ncap, a->ngroups));
+        agg_fill_params(a, &sb, &P);
+        {
+            KernelScope ks(ctx, "agg_rehash");
+            k_agg_rehash<<<grid_rows(ctx, a->ngroups, 256, 8), 256, 0, ctx->stream>>>(P, a->ngroups);
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+        P.row_list = pending.as<int64_t>();
+        P.rows = nover;
+    }
+    if (batch->mem == GSQL_MEM_HOST) GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_agg_output_schema(gsql_agg *a, int32_t *ncols, int32_t *types) {
+    if (!a || !ncols) return GSQL_E_INVALID;
+    *ncols = a->nout;
+    if (types)
+        for (int i = 0; i < a->nout; i++) types[i] = a->out_types[i];
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_agg_finish(gsql_agg *a, int64_t *ngroups) {
+    if (!a) return GSQL_E_INVALID;
+    gsql_ctx *ctx = a->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!a->finished) {
+        int64_t n = a->ngroups;
+        FinalParams F;
+        memset(&F, 0, sizeof(F));
+        F.nkeys = a->nkeys;
+        F.naggs = a->naggs;
+        F.ngroups = n;
+        AggParams P;
+        agg_fill_params(a, nullptr, &P);
+        for (int k = 0; k < a->nkeys; k++) {
+            F.gkey[k] = P.gkey[k];
+            F.gnull[k] = P.gnull[k];
+            F.key_types[k] = a->out_types[k];
+        }
+        for (int i = 0; i < a->naggs; i++) F.agg[i] = P.agg[i];
+        for (int c = 0; c < a->nout; c++) {
+            GSQL_TRY(a->out_data[c].alloc(ctx, (size_t)(n > 0 ? n : 1) * gsql_type_width(a->out_types[c])));
+            GSQL_TRY(a->out_nulls[c].alloc(ctx, (size_t)(n > 0 ? n : 1)));
+            F.out[c].data = a->out_data[c].p;
+            F.out[c].nulls = a->out_nulls[c].as<uint8_t>();
+            F.out[c].type = a->out_types[c];
+        }
+        if (n > 0) {
+            KernelScope ks(ctx, "agg_finalize");
+            k_agg_finalize<<<grid_rows(ctx, n, 256, 8), 256, 0, ctx->stream>>>(F);
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+        a->finished = true;
+        a->cursor = 0;
+    }
+    if (ngroups) *ngroups = a->ngroups;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_agg_next(gsql_agg *a, gsql_batch *out, int64_t max_rows, int64_t *out_rows) {
+    if (!a || !out || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = a->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (!a->finished) return gsql_set_error(ctx, GSQL_E_STATE, "next before finish");
+    GSQL_TRY(validate_batch(ctx, out, a->nout, a->out_types));
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t n = a->ngroups - a->cursor;
+    if (n > max_rows) n = max_rows;
+    if (n < 0) n = 0;
+    *out_rows = n;
+    out->rows = n;
+    if (n == 0) return GSQL_OK;
+    cudaMemcpyKind kind = out->mem == GSQL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int c = 0; c < a->nout; c++) {
+        int w = gsql_type_width(a->out_types[c]);
+        if (!out->cols[c].nulls) return gsql_set_error(ctx, GSQL_E_INVALID, "agg output column %d needs a nulls buffer", c);
+        GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[c].data, (char *)a->out_data[c].p + (size_t)a->cursor * w, (size_t)n * w, kind, ctx->stream));
+        GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[c].nulls, (char *)a->out_nulls[c].p + a->cursor, (size_t)n, kind, ctx->stream));
+    }
+    if (out->mem == GSQL_MEM_HOST) GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    a->cursor += n;
+    return GSQL_OK;
+}

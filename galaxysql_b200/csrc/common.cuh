@@ -1,0 +1,258 @@
+// common.cuh — shared host/device pieces of libgsql_gpu.so (sm_100a only).
+//
+// Hash restatements are bit-exact with the reference (file:line cited at each function) because they are
+// observable across the exchange boundary (a GPU task and a stock Java task must route a row to the same
+// consumer).  The join / group-by tables themselves are NOT the reference's structures: only the result
+// multiset is contractual (BaseExecTest.java:78-103), so they are laid out for HBM sectors instead.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/gsql_gpu.h"
+
+// ------------------------------------------------------------------------------------------------ context
+struct ProfEntry {
+    std::string name;
+    int64_t launches = 0;
+    double ms = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct gsql_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_in = nullptr;   // H2D staging stream (e2e path)
+    cudaStream_t copy_out = nullptr;  // D2H staging stream
+    char err[1024] = {0};
+    bool sticky = false;
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::vector<cudaEvent_t> event_pool;
+    int64_t launches = 0;
+    void *nccl_comm = nullptr;  // ncclComm_t
+    int nranks = 1, rank = 0;
+    int sm_count = 148;
+};
+
+gsql_status gsql_set_error(gsql_ctx *ctx, gsql_status st, const char *fmt, ...);
+
+#define GSQL_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                       \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            (ctx)->sticky = true;                                                                              \
+            return gsql_set_error((ctx), _e == cudaErrorMemoryAllocation ? GSQL_E_OOM : GSQL_E_CUDA,           \
+                                  "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));        \
+        }                                                                                                      \
+    } while (0)
+
+#define GSQL_TRY(expr)                    \
+    do {                                  \
+        gsql_status _s = (expr);          \
+        if (_s != GSQL_OK) return _s;     \
+    } while (0)
+
+// RAII scope that times one named kernel launch with CUDA events on the launching stream (profiling only) and
+// counts the launch.  Usage:  { KernelScope ks(ctx, "join_probe"); kernel<<<g, b, 0, ctx->stream>>>(...); }
+struct KernelScope {
+    gsql_ctx *ctx;
+    int idx = -1;
+    cudaEvent_t start = nullptr;
+    KernelScope(gsql_ctx *c, const char *name);
+    ~KernelScope();
+};
+
+// Stream-ordered device memory (cudaMallocAsync on the context stream).
+gsql_status dev_alloc(gsql_ctx *ctx, size_t bytes, void **out);
+void dev_free(gsql_ctx *ctx, void *p);
+
+struct DevBuf {
+    gsql_ctx *ctx = nullptr;
+    void *p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p && ctx) dev_free(ctx, p);
+        p = nullptr;
+        bytes = 0;
+    }
+    gsql_status alloc(gsql_ctx *c, size_t n) {
+        release();
+        ctx = c;
+        if (n == 0) n = 16;
+        gsql_status s = dev_alloc(c, n, &p);
+        if (s == GSQL_OK) bytes = n;
+        return s;
+    }
+    // Grow keeping the first `keep` bytes.
+    gsql_status grow(gsql_ctx *c, size_t n, size_t keep) {
+        if (n <= bytes) return GSQL_OK;
+        void *np = nullptr;
+        gsql_status s = dev_alloc(c, n, &np);
+        if (s != GSQL_OK) return s;
+        if (p && keep) {
+            cudaError_t e = cudaMemcpyAsync(np, p, keep, cudaMemcpyDeviceToDevice, c->stream);
+            if (e != cudaSuccess) return gsql_set_error(c, GSQL_E_CUDA, "grow copy: %s", cudaGetErrorString(e));
+        }
+        if (p) dev_free(c, p);
+        ctx = c;
+        p = np;
+        bytes = n;
+        return GSQL_OK;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------------------------------------ columns
+__host__ __device__ inline int gsql_type_width(int t) { return t == GSQL_T_INT32 ? 4 : (t == GSQL_T_DEC128 ? 16 : 8); }
+
+struct DCol {  // a Block resident in HBM
+    const void *data;
+    const uint8_t *nulls;  // nullptr = no NULLs
+    int32_t type;
+    int32_t pad;
+};
+
+struct DColSet {
+    int32_t n;
+    int32_t pad;
+    DCol c[GSQL_MAX_COLS];
+};
+
+struct KeySet {  // key columns with their unified type (EquiJoinKey.unifiedType / keyTargetTypes)
+    int32_t n;
+    int32_t pad;
+    DCol c[GSQL_MAX_KEYS];
+    int32_t utype[GSQL_MAX_KEYS];
+};
+
+// A batch staged in HBM: aliases device input or owns uploaded copies of host input.
+struct StagedBatch {
+    int64_t rows = 0;
+    int32_t ncols = 0;
+    DCol cols[GSQL_MAX_COLS];
+    std::vector<DevBuf *> owned;
+    ~StagedBatch() {
+        for (auto *b : owned) delete b;
+    }
+};
+gsql_status stage_batch(gsql_ctx *ctx, const gsql_batch *in, StagedBatch *out);
+gsql_status validate_batch(gsql_ctx *ctx, const gsql_batch *b, int32_t expect_cols, const int32_t *expect_types);
+
+// ------------------------------------------------------------------------------------------------ hashing
+// fastutil HashCommon.mix (call sites ConcurrentRawHashTable.java:93,114; GroupOpenHashMap.java:143)
+__host__ __device__ __forceinline__ int32_t gsql_mix(int32_t x) {
+    uint32_t h = (uint32_t)x * 0x9E3779B9u;
+    return (int32_t)(h ^ (h >> 16));
+}
+// fastutil HashCommon.murmurHash3 (call site ExecUtils.java:1026,1029)
+__host__ __device__ __forceinline__ int32_t gsql_murmur3(int32_t xi) {
+    uint32_t x = (uint32_t)xi;
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return (int32_t)x;
+}
+// ExecUtils.partition (EX/utils/ExecUtils.java:1023-1031)
+__host__ __device__ __forceinline__ int32_t gsql_partition_of(int32_t hash, int32_t nparts, bool pow2) {
+    uint32_t m = (uint32_t)gsql_murmur3(hash);
+    return pow2 ? (int32_t)(m & (uint32_t)(nparts - 1)) : (int32_t)((m & 0x7fffffffu) % (uint32_t)nparts);
+}
+// Long.hashCode (LongBlock.java:110-115)
+__host__ __device__ __forceinline__ int32_t gsql_hash_i64(int64_t v) {
+    uint64_t u = (uint64_t)v;
+    return (int32_t)(uint32_t)(u ^ (u >> 32));
+}
+// Double.doubleToLongBits: NaN canonicalised (DoubleBlock.java:111-116)
+__device__ __forceinline__ int64_t gsql_double_bits(double d) {
+    return d != d ? 0x7ff8000000000000LL : __double_as_longlong(d);
+}
+
+struct KeyVal {
+    int64_t i;  // integer value, or raw double bits for FP64
+    bool is_null;
+};
+
+// Reads key column c at row r converted to its unified type (Converters.java:94-131): integer widening or
+// (double) cast.  For FP64 the value travels as raw (non-canonicalised) bits.
+__device__ __forceinline__ KeyVal gsql_load_key(const DCol &c, int64_t r, int utype) {
+    KeyVal k;
+    k.is_null = c.nulls != nullptr && c.nulls[r] != 0;
+    k.i = 0;
+    if (k.is_null) return k;
+    if (utype == GSQL_T_FP64) {
+        double d;
+        if (c.type == GSQL_T_FP64) d = reinterpret_cast<const double *>(c.data)[r];
+        else if (c.type == GSQL_T_INT64) d = (double)reinterpret_cast<const int64_t *>(c.data)[r];
+        else d = (double)reinterpret_cast<const int32_t *>(c.data)[r];
+        k.i = __double_as_longlong(d);
+    } else {
+        if (c.type == GSQL_T_INT32) k.i = reinterpret_cast<const int32_t *>(c.data)[r];
+        else if (c.type == GSQL_T_INT64) k.i = reinterpret_cast<const int64_t *>(c.data)[r];
+        else k.i = (int64_t)reinterpret_cast<const double *>(c.data)[r];
+    }
+    return k;
+}
+// Block.hashCode(position) per unified type; NULL -> 0 (Block.java:113-118, IntegerBlock.java:112-117)
+__device__ __forceinline__ int32_t gsql_key_hash(const KeyVal &k, int utype) {
+    if (k.is_null) return 0;
+    if (utype == GSQL_T_INT32) return (int32_t)k.i;
+    if (utype == GSQL_T_FP64) return gsql_hash_i64(gsql_double_bits(__longlong_as_double(k.i)));
+    return gsql_hash_i64(k.i);
+}
+// Chunk.hashCode(position): h = h*31 + block.hashCode (Chunk.java:124-130)
+__device__ __forceinline__ int32_t gsql_row_hash(const KeySet &ks, int64_t r) {
+    uint32_t h = 0;
+#pragma unroll 1
+    for (int c = 0; c < ks.n; c++) {
+        KeyVal k = gsql_load_key(ks.c[c], r, ks.utype[c]);
+        h = h * 31u + (uint32_t)gsql_key_hash(k, ks.utype[c]);
+    }
+    return (int32_t)h;
+}
+
+// 64-bit finaliser used for table placement (not contractual).
+__host__ __device__ __forceinline__ uint64_t gsql_fmix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------ memory ops
+// Streaming (read-once) loads / write-once stores: keep them out of L1 and first in line for L2 eviction so
+// that hash-table sectors stay resident.
+__device__ __forceinline__ int4 ld_stream_16(const void *p) {
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_16(void *p, const int4 &v) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+                 "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_8(void *p, long long v) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream_4(void *p, int v) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

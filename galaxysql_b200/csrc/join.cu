@@ -1,0 +1,801 @@
+// join.cu — GPU hash join behind gsql_join_* (drop-in for ParallelHashJoinExec build + probe).
+//
+// Reference path replaced (EX/ = polardbx-executor/src/main/java/com/alibaba/polardbx/executor/):
+//   build : EX/operator/ParallelHashJoinExec.java:157-166 (consumeChunk), :107-128 (buildConsume), :388-426
+//           (Synchronizer.initHashTable/buildHashTable), EX/utils/ExecUtils.java:914-944 (buildOneChunk),
+//           EX/operator/util/ConcurrentRawHashTable.java:50-116
+//   probe : EX/operator/AbstractBufferedJoinExec.java:185-264 (nextRows), AbstractHashJoinExec.java:80-106
+//           (matchInit/matchNext), AbstractJoinExec.java:174-227 (row builders),
+//           ParallelHashJoinExec.java:168-201,233-271 (outer-build variants)
+//
+// B200 layout (not the reference's): one open-addressing table of 16-byte slots {digest, chain head, multi flag}
+// in HBM, two slots per 32-byte sector, load factor <= 0.5, slot = mulhi(fmix64(digest), nslots).  For a single
+// key column the digest IS the key (exact, no verification read); for composite keys it is a 64-bit mix verified
+// against the build columns.  Duplicate build keys hang off the slot as a LIFO chain through links[] exactly like
+// positionLinks, and the `multi` flag lets the unique-key probe skip links[] entirely.
+// Output is produced in two passes (count -> exclusive scan -> write) so it is dense and exactly sized.
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "common.cuh"
+#include "join_fast.cuh"
+
+namespace {
+
+constexpr unsigned long long DIGEST_EMPTY = 0x8000000000000000ULL;
+enum { F_ANY_MULTI = 0, F_MORE_THAN_ONE = 1, F_NULL_INTO_NONNULL = 2, F_COUNT = 4 };
+enum { SIDE_PROBE = 0, SIDE_BUILD = 1 };
+
+struct __align__(16) Slot {
+    unsigned long long digest;
+    int head;
+    int multi;
+};
+
+struct OutCol {
+    void *data;
+    uint8_t *nulls;
+    int32_t type;
+    int32_t side;
+    int32_t col;
+    int32_t pad;
+};
+
+struct ProbeParams {
+    KeySet bkeys, pkeys;
+    DColSet build, probe;
+    const Slot *slots;
+    const int32_t *links;
+    uint8_t *used;  // build_outer: matched flags
+    int32_t *flags;
+    uint64_t nslots;
+    int64_t probe_rows;
+    int32_t join_type, single_join, semi_join, outer_join, build_outer, exact;
+    int32_t n_anti;
+    int32_t anti_cols[GSQL_MAX_KEYS];
+    int32_t n_cond;
+    int32_t cond_side[4], cond_col[4];
+    int64_t cond_ne[4];
+    int32_t nout;
+    OutCol out[GSQL_MAX_COLS * 2];
+};
+
+// ------------------------------------------------------------------------------------------------ digests
+// false => this row can never match (NULL key component, or NaN: Java `==` is false for NaN — DoubleBlock.java:77-91)
+__device__ __forceinline__ bool key_digest(const KeySet &ks, int64_t r, unsigned long long &d) {
+    if (ks.n == 1) {
+        KeyVal k = gsql_load_key(ks.c[0], r, ks.utype[0]);
+        if (k.is_null) return false;
+        if (ks.utype[0] == GSQL_T_FP64) {
+            double v = __longlong_as_double(k.i);
+            if (v != v) return false;
+            if (v == 0.0) k.i = 0;  // -0.0 == 0.0
+        }
+        d = (unsigned long long)k.i;
+        return true;
+    }
+    unsigned long long h = 0x243F6A8885A308D3ULL;
+#pragma unroll 1
+    for (int c = 0; c < ks.n; c++) {
+        KeyVal k = gsql_load_key(ks.c[c], r, ks.utype[c]);
+        if (k.is_null) return false;
+        if (ks.utype[c] == GSQL_T_FP64) {
+            double v = __longlong_as_double(k.i);
+            if (v != v) return false;
+            if (v == 0.0) k.i = 0;
+        }
+        h = gsql_fmix64(h ^ (unsigned long long)k.i) + 0x9E3779B97F4A7C15ULL * (unsigned)(c + 1);
+    }
+    if (h == DIGEST_EMPTY) h ^= 1;
+    d = h;
+    return true;
+}
+
+__device__ __forceinline__ uint64_t slot_start(unsigned long long d, uint64_t nslots) {
+    return __umul64hi(gsql_fmix64(d), nslots);
+}
+
+__device__ __forceinline__ bool keys_equal(const KeySet &a, int64_t ra, const KeySet &b, int64_t rb) {
+#pragma unroll 1
+    for (int c = 0; c < a.n; c++) {
+        KeyVal x = gsql_load_key(a.c[c], ra, a.utype[c]);
+        KeyVal y = gsql_load_key(b.c[c], rb, b.utype[c]);
+        if (x.is_null || y.is_null) return false;  // NULL components were never inserted / never probe
+        if (a.utype[c] == GSQL_T_FP64) {
+            if (!(__longlong_as_double(x.i) == __longlong_as_double(y.i))) return false;
+        } else if (x.i != y.i) return false;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ build
+__global__ void __launch_bounds__(256) k_slots_init(Slot *slots, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        int4 v;
+        v.x = 0;
+        v.y = (int)0x80000000;  // digest = 0x8000000000000000 (little endian: low word first)
+        v.z = -1;               // head
+        v.w = 0;                // multi
+        reinterpret_cast<int4 *>(slots)[i] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    k_join_build(KeySet bkeys, int64_t build_rows, Slot *slots, uint64_t nslots, int32_t *links, int32_t *flags) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < build_rows; p += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long d;
+        if (!key_digest(bkeys, p, d)) {  // ExecUtils.java:932-941: rows with a NULL key are never inserted
+            links[p] = -1;
+            continue;
+        }
+        uint64_t s;
+        if (d == DIGEST_EMPTY) {
+            s = nslots;  // dedicated slot for the one key that equals the empty marker
+        } else {
+            s = slot_start(d, nslots);
+            while (true) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&slots[s].digest);
+                if (cur == DIGEST_EMPTY) {
+                    unsigned long long prev = atomicCAS(&slots[s].digest, DIGEST_EMPTY, d);
+                    if (prev == DIGEST_EMPTY || prev == d) break;
+                } else if (cur == d) {
+                    break;
+                }
+                if (++s == nslots) s = 0;
+            }
+        }
+        int old = atomicExch(&slots[s].head, (int)p);  // newest row becomes the chain head (LIFO, like put())
+        links[p] = old;
+        if (old != -1) {
+            slots[s].multi = 1;
+            flags[F_ANY_MULTI] = 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ probe
+__device__ __forceinline__ bool col_null(const DCol &c, int64_t r) { return c.nulls != nullptr && c.nulls[r] != 0; }
+
+__device__ __forceinline__ int64_t col_int(const DCol &c, int64_t r) {
+    if (c.type == GSQL_T_INT32) return reinterpret_cast<const int32_t *>(c.data)[r];
+    if (c.type == GSQL_T_INT64) return reinterpret_cast<const int64_t *>(c.data)[r];
+    return (int64_t) reinterpret_cast<const double *>(c.data)[r];
+}
+
+__device__ __forceinline__ void put_null(const ProbeParams &P, const OutCol &o, int64_t pos) {
+    if (o.nulls) o.nulls[pos] = 1;
+    else P.flags[F_NULL_INTO_NONNULL] = 1;
+    if (o.type == GSQL_T_INT32) reinterpret_cast<int32_t *>(o.data)[pos] = 0;
+    else reinterpret_cast<int64_t *>(o.data)[pos] = 0;
+}
+
+__device__ __forceinline__ void put_from(const ProbeParams &P, const OutCol &o, int64_t pos, const DCol &src, int64_t sr) {
+    if (col_null(src, sr)) {
+        put_null(P, o, pos);
+        return;
+    }
+    if (o.nulls) o.nulls[pos] = 0;
+    if (o.type == GSQL_T_INT32) reinterpret_cast<int32_t *>(o.data)[pos] = reinterpret_cast<const int32_t *>(src.data)[sr];
+    else reinterpret_cast<int64_t *>(o.data)[pos] = reinterpret_cast<const int64_t *>(src.data)[sr];
+}
+
+// WRITE=false: returns the number of rows probe row r emits.  WRITE=true: writes them starting at `base`.
+template <bool WRITE>
+__device__ __forceinline__ int probe_one(const ProbeParams &P, int64_t r, int64_t base) {
+    int emitted = 0;
+    bool matched = false;
+    unsigned long long d;
+    if (key_digest(P.pkeys, r, d)) {
+        // ---- find the slot of this digest (linear probing, stops at an empty slot)
+        int head = -1, multi = 0;
+        if (d == DIGEST_EMPTY) {
+            Slot sl = P.slots[P.nslots];
+            head = sl.head;
+            multi = sl.multi;
+        } else {
+            uint64_t s = slot_start(d, P.nslots);
+            while (true) {
+                int4 raw = __ldg(reinterpret_cast<const int4 *>(&P.slots[s]));
+                unsigned long long dg = ((unsigned long long)(unsigned)raw.y << 32) | (unsigned)raw.x;
+                if (dg == d) {
+                    head = raw.z;
+                    multi = raw.w;
+                    break;
+                }
+                if (dg == DIGEST_EMPTY) break;
+                if (++s == P.nslots) s = 0;
+            }
+        }
+        // ---- walk the chain (matchInit / matchNext)
+        for (int m = head; m != -1; m = multi ? P.links[m] : -1) {
+            if (!P.exact && !keys_equal(P.bkeys, m, P.pkeys, r)) continue;
+            if (P.n_cond) {  // restricted otherCondition: joinRow[c] IS NULL OR joinRow[c] != v
+                bool ok = true;
+                for (int i = 0; i < P.n_cond && ok; i++) {
+                    const DCol &c = P.cond_side[i] == SIDE_PROBE ? P.probe.c[P.cond_col[i]] : P.build.c[P.cond_col[i]];
+                    int64_t row = P.cond_side[i] == SIDE_PROBE ? r : (int64_t)m;
+                    if (!col_null(c, row) && col_int(c, row) == P.cond_ne[i]) ok = false;
+                }
+                if (!ok) continue;
+            }
+            if (!P.semi_join) {  // INNER / LEFT / RIGHT emit one joined row per match
+                if (WRITE) {
+                    int64_t pos = base + emitted;
+                    for (int q = 0; q < P.nout; q++) {
+                        const OutCol &o = P.out[q];
+                        if (o.side == SIDE_PROBE) put_from(P, o, pos, P.probe.c[o.col], r);
+                        else put_from(P, o, pos, P.build.c[o.col], m);
+                    }
+                    if (P.build_outer) P.used[m] = 1;  // markUsedKeys
+                }
+                emitted++;
+            }
+            if (P.single_join && matched) P.flags[F_MORE_THAN_ONE] = 1;  // AbstractBufferedJoinExec.java:217-219
+            matched = true;
+            if (P.semi_join) break;
+        }
+    }
+    if (P.outer_join && !P.build_outer && !matched) {  // buildLeftNullRow / buildRightNullRow
+        if (WRITE) {
+            int64_t pos = base + emitted;
+            for (int q = 0; q < P.nout; q++) {
+                const OutCol &o = P.out[q];
+                if (o.side == SIDE_PROBE) put_from(P, o, pos, P.probe.c[o.col], r);
+                else put_null(P, o, pos);
+            }
+        }
+        emitted++;
+    }
+    if (P.semi_join) {
+        bool emit = false;
+        if (P.join_type == GSQL_JOIN_SEMI) emit = matched;
+        else if (!matched) {  // ANTI; checkAntiJoinOperands (AbstractJoinExec.java:126-136)
+            emit = true;
+            for (int i = 0; i < P.n_anti; i++)
+                if (col_null(P.probe.c[P.anti_cols[i]], r)) emit = false;
+        }
+        if (emit) {
+            if (WRITE) {
+                int64_t pos = base + emitted;
+                for (int q = 0; q < P.nout; q++) put_from(P, P.out[q], pos, P.probe.c[P.out[q].col], r);
+            }
+            emitted++;
+        }
+    }
+    return emitted;
+}
+
+__global__ void __launch_bounds__(256) k_probe_count(const __grid_constant__ ProbeParams P, int32_t *__restrict__ cnt) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < P.probe_rows; r += (int64_t)gridDim.x * blockDim.x)
+        cnt[r] = probe_one<false>(P, r, 0);
+}
+
+__global__ void __launch_bounds__(256) k_probe_write(const __grid_constant__ ProbeParams P, const int64_t *__restrict__ off) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < P.probe_rows; r += (int64_t)gridDim.x * blockDim.x)
+        probe_one<true>(P, r, off[r]);
+}
+
+// unmatched build rows of an outer build (nextJoinNullRows)
+__global__ void __launch_bounds__(256)
+    k_unmatched_count(const uint8_t *__restrict__ used, int64_t rows, int32_t *__restrict__ cnt) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)
+        cnt[r] = used[r] ? 0 : 1;
+}
+__global__ void __launch_bounds__(256) k_unmatched_write(const __grid_constant__ ProbeParams P, int64_t build_rows,
+                                                         const int64_t *__restrict__ off) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < build_rows; p += (int64_t)gridDim.x * blockDim.x) {
+        if (P.used[p]) continue;
+        int64_t pos = off[p];
+        for (int q = 0; q < P.nout; q++) {
+            const OutCol &o = P.out[q];
+            if (o.side == SIDE_BUILD) put_from(P, o, pos, P.build.c[o.col], p);
+            else put_null(P, o, pos);
+        }
+    }
+}
+
+struct ToI64 {
+    __host__ __device__ int64_t operator()(const int32_t &v) const { return (int64_t)v; }
+};
+
+}  // namespace
+
+// ================================================================================================ handle
+struct gsql_join {
+    gsql_ctx *ctx;
+    gsql_join_spec spec;
+    bool built = false;
+    // build side
+    int32_t n_build = 0, n_probe = 0;
+    int32_t build_types[GSQL_MAX_COLS], probe_types[GSQL_MAX_COLS];
+    int32_t bkey_cols[GSQL_MAX_KEYS], pkey_cols[GSQL_MAX_KEYS];
+    DevBuf bdata[GSQL_MAX_COLS], bnulls[GSQL_MAX_COLS];
+    bool bhas_nulls[GSQL_MAX_COLS];
+    int64_t build_rows = 0, build_cap = 0;
+    // table
+    DevBuf slots, links, used, flags;
+    uint64_t nslots = 0;
+    bool any_multi = false;
+    bool pass_nothing = false, pass_through = false;
+    bool semi_join = false, outer_join = false, single_join = false;
+    // output schema
+    int32_t nout = 0;
+    int32_t out_types[GSQL_MAX_COLS * 2];
+    int32_t out_side[GSQL_MAX_COLS * 2], out_col[GSQL_MAX_COLS * 2];
+    int32_t cond_side[4], cond_col[4];
+    // fast path (join_fast.cuh)
+    JoinFast fast;
+};
+
+static int grid_rows(gsql_ctx *ctx, int64_t rows, int block, int per_sm) {
+    int64_t g = div_up(rows, block);
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+extern "C" gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spec, gsql_join **out) {
+    if (!ctx || !spec || !out) return GSQL_E_INVALID;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    *out = nullptr;
+    const gsql_join_spec &s = *spec;
+    if (s.join_type < GSQL_JOIN_INNER || s.join_type > GSQL_JOIN_ANTI) return gsql_set_error(ctx, GSQL_E_INVALID, "bad join type");
+    if (s.nkeys < 1 || s.nkeys > GSQL_MAX_KEYS) return gsql_set_error(ctx, GSQL_E_INVALID, "need 1..%d equi keys", GSQL_MAX_KEYS);
+    if (s.n_outer_cols < 1 || s.n_outer_cols > GSQL_MAX_COLS || s.n_inner_cols < 1 || s.n_inner_cols > GSQL_MAX_COLS)
+        return gsql_set_error(ctx, GSQL_E_INVALID, "bad column counts");
+    bool semi = (s.join_type == GSQL_JOIN_SEMI || s.join_type == GSQL_JOIN_ANTI) && !s.max_one_row;
+    if ((s.join_type == GSQL_JOIN_SEMI || s.join_type == GSQL_JOIN_ANTI) && s.max_one_row)
+        return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "single (max-one-row) semi/anti join");
+    if (s.build_outer && (semi || s.n_cond > 0)) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "build_outer with semi/anti/condition");
+    if (s.n_cond < 0 || s.n_cond > 4 || s.n_anti_operands < 0 || s.n_anti_operands > GSQL_MAX_KEYS)
+        return gsql_set_error(ctx, GSQL_E_INVALID, "bad condition / anti operand count");
+    for (int i = 0; i < s.n_outer_cols; i++)
+        if (s.outer_types[i] < GSQL_T_INT32 || s.outer_types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "outer col %d type", i);
+    for (int i = 0; i < s.n_inner_cols; i++)
+        if (s.inner_types[i] < GSQL_T_INT32 || s.inner_types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "inner col %d type", i);
+    for (int i = 0; i < s.nkeys; i++) {
+        if (s.outer_key[i] < 0 || s.outer_key[i] >= s.n_outer_cols || s.inner_key[i] < 0 || s.inner_key[i] >= s.n_inner_cols)
+            return gsql_set_error(ctx, GSQL_E_INVALID, "key %d out of range", i);
+        if (s.key_type[i] < GSQL_T_INT32 || s.key_type[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_INVALID, "key %d type", i);
+    }
+    for (int i = 0; i < s.n_anti_operands; i++)
+        if (s.anti_operands[i] < 0 || s.anti_operands[i] >= s.n_outer_cols) return gsql_set_error(ctx, GSQL_E_INVALID, "anti operand");
+
+    gsql_join *j = new gsql_join();
+    j->ctx = ctx;
+    j->spec = s;
+    j->semi_join = semi;
+    j->single_join = s.max_one_row != 0;
+    j->outer_join = s.join_type == GSQL_JOIN_LEFT || s.join_type == GSQL_JOIN_RIGHT;
+    const bool bo = s.build_outer != 0;
+    j->n_build = bo ? s.n_outer_cols : s.n_inner_cols;
+    j->n_probe = bo ? s.n_inner_cols : s.n_outer_cols;
+    for (int i = 0; i < j->n_build; i++) j->build_types[i] = bo ? s.outer_types[i] : s.inner_types[i];
+    for (int i = 0; i < j->n_probe; i++) j->probe_types[i] = bo ? s.inner_types[i] : s.outer_types[i];
+    for (int i = 0; i < s.nkeys; i++) {
+        j->bkey_cols[i] = bo ? s.outer_key[i] : s.inner_key[i];
+        j->pkey_cols[i] = bo ? s.inner_key[i] : s.outer_key[i];
+    }
+    for (int i = 0; i < GSQL_MAX_COLS; i++) j->bhas_nulls[i] = false;
+    // ---- output schema (AbstractJoinExec.java:103-120); outer -> probe unless build_outer
+    const int outer_side = bo ? SIDE_BUILD : SIDE_PROBE, inner_side = bo ? SIDE_PROBE : SIDE_BUILD;
+    auto push = [&](int side, int col, int type) {
+        j->out_side[j->nout] = side;
+        j->out_col[j->nout] = col;
+        j->out_types[j->nout] = type;
+        j->nout++;
+    };
+    if (semi) {
+        for (int i = 0; i < s.n_outer_cols; i++) push(outer_side, i, s.outer_types[i]);
+    } else if (j->single_join) {
+        for (int i = 0; i < s.n_outer_cols; i++) push(outer_side, i, s.outer_types[i]);
+        push(inner_side, 0, s.inner_types[0]);
+    } else if (s.join_type == GSQL_JOIN_RIGHT) {
+        for (int i = 0; i < s.n_inner_cols; i++) push(inner_side, i, s.inner_types[i]);
+        for (int i = 0; i < s.n_outer_cols; i++) push(outer_side, i, s.outer_types[i]);
+    } else {
+        for (int i = 0; i < s.n_outer_cols; i++) push(outer_side, i, s.outer_types[i]);
+        for (int i = 0; i < s.n_inner_cols; i++) push(inner_side, i, s.inner_types[i]);
+    }
+    // condition columns index the full join row leftSide || rightSide
+    for (int i = 0; i < s.n_cond; i++) {
+        int c = s.cond_col[i];
+        int nleft = s.join_type == GSQL_JOIN_RIGHT ? s.n_inner_cols : s.n_outer_cols;
+        int left_side = s.join_type == GSQL_JOIN_RIGHT ? inner_side : outer_side;
+        int right_side = s.join_type == GSQL_JOIN_RIGHT ? outer_side : inner_side;
+        if (c < 0 || c >= s.n_outer_cols + s.n_inner_cols) { delete j; return gsql_set_error(ctx, GSQL_E_INVALID, "cond col"); }
+        j->cond_side[i] = c < nleft ? left_side : right_side;
+        j->cond_col[i] = c < nleft ? c : c - nleft;
+        int t = j->cond_side[i] == SIDE_PROBE ? j->probe_types[j->cond_col[i]] : j->build_types[j->cond_col[i]];
+        if (t == GSQL_T_FP64) { delete j; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "condition on a double column"); }
+    }
+    if (j->flags.alloc(ctx, F_COUNT * sizeof(int32_t)) != GSQL_OK) { delete j; return GSQL_E_OOM; }
+    cudaMemsetAsync(j->flags.p, 0, j->flags.bytes, ctx->stream);
+    *out = j;
+    return GSQL_OK;
+}
+
+extern "C" void gsql_join_destroy(gsql_join *j) {
+    if (!j) return;
+    cudaSetDevice(j->ctx->device);
+    delete j;
+}
+
+static gsql_status join_reserve(gsql_join *j, int64_t need) {
+    if (need <= j->build_cap) return GSQL_OK;
+    int64_t cap = j->build_cap ? j->build_cap : 1024;
+    if (j->spec.expected_build_rows > cap) cap = j->spec.expected_build_rows;
+    while (cap < need) cap *= 2;
+    gsql_ctx *ctx = j->ctx;
+    for (int i = 0; i < j->n_build; i++) {
+        int w = gsql_type_width(j->build_types[i]);
+        GSQL_TRY(j->bdata[i].grow(ctx, (size_t)cap * w, (size_t)j->build_rows * w));
+        if (j->bhas_nulls[i]) GSQL_TRY(j->bnulls[i].grow(ctx, (size_t)cap, (size_t)j->build_rows));
+    }
+    j->build_cap = cap;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_join_build_consume(gsql_join *j, const gsql_batch *b) {
+    if (!j) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (j->built) return gsql_set_error(ctx, GSQL_E_STATE, "build_consume after build_finish");
+    GSQL_TRY(validate_batch(ctx, b, j->n_build, j->build_types));
+    if (b->rows == 0) return GSQL_OK;
+    if (j->build_rows + b->rows > 0x7fffffffLL) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "build side exceeds 2^31-1 rows");
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    GSQL_TRY(join_reserve(j, j->build_rows + b->rows));
+    cudaMemcpyKind kind = b->mem == GSQL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int i = 0; i < j->n_build; i++) {
+        int w = gsql_type_width(j->build_types[i]);
+        GSQL_CUDA(ctx, cudaMemcpyAsync((char *)j->bdata[i].p + (size_t)j->build_rows * w, b->cols[i].data, (size_t)b->rows * w, kind, ctx->stream));
+        if (b->cols[i].nulls) {
+            if (!j->bhas_nulls[i]) {  // first batch with NULLs in this column: materialise the mask, zero history
+                GSQL_TRY(j->bnulls[i].alloc(ctx, (size_t)j->build_cap));
+                GSQL_CUDA(ctx, cudaMemsetAsync(j->bnulls[i].p, 0, (size_t)j->build_cap, ctx->stream));
+                j->bhas_nulls[i] = true;
+            }
+            GSQL_CUDA(ctx, cudaMemcpyAsync((char *)j->bnulls[i].p + j->build_rows, b->cols[i].nulls, (size_t)b->rows, kind, ctx->stream));
+        } else if (j->bhas_nulls[i]) {
+            GSQL_CUDA(ctx, cudaMemsetAsync((char *)j->bnulls[i].p + j->build_rows, 0, (size_t)b->rows, ctx->stream));
+        }
+    }
+    if (b->mem == GSQL_MEM_HOST) GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // caller may reuse its buffers
+    j->build_rows += b->rows;
+    return GSQL_OK;
+}
+
+static void fill_build_cols(gsql_join *j, DColSet *build, KeySet *bkeys) {
+    build->n = j->n_build;
+    for (int i = 0; i < j->n_build; i++) {
+        build->c[i].data = j->bdata[i].p;
+        build->c[i].nulls = j->bhas_nulls[i] ? j->bnulls[i].as<uint8_t>() : nullptr;
+        build->c[i].type = j->build_types[i];
+        build->c[i].pad = 0;
+    }
+    bkeys->n = j->spec.nkeys;
+    for (int i = 0; i < j->spec.nkeys; i++) {
+        bkeys->c[i] = build->c[j->bkey_cols[i]];
+        bkeys->utype[i] = j->spec.key_type[i];
+    }
+}
+
+extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
+    if (!j) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (j->built) return GSQL_OK;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const gsql_join_spec &s = j->spec;
+    // pass-through / pass-nothing (ParallelHashJoinExec.buildConsume:107-128; doSpecialCheckForSemiJoin:290-310)
+    if (j->build_rows == 0 && s.join_type == GSQL_JOIN_INNER) j->pass_nothing = true;
+    if (j->semi_join) {
+        if (j->build_rows == 0) {
+            if (s.join_type == GSQL_JOIN_SEMI) j->pass_nothing = true;
+            else j->pass_through = true;
+        } else if (s.join_type == GSQL_JOIN_ANTI && s.n_anti_operands > 0 && j->n_build == 1 && j->bhas_nulls[0]) {
+            // x NOT IN (... NULL ...) is never true: need to know whether the single build column holds a NULL
+            std::vector<uint8_t> h((size_t)j->build_rows);
+            GSQL_CUDA(ctx, cudaMemcpyAsync(h.data(), j->bnulls[0].p, (size_t)j->build_rows, cudaMemcpyDeviceToHost, ctx->stream));
+            GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint8_t v : h)
+                if (v) { j->pass_nothing = true; break; }
+        }
+    }
+    j->nslots = (uint64_t)(j->build_rows * 2 > 64 ? j->build_rows * 2 : 64);
+    GSQL_TRY(j->slots.alloc(ctx, (size_t)(j->nslots + 1) * sizeof(Slot)));
+    GSQL_TRY(j->links.alloc(ctx, (size_t)(j->build_rows > 0 ? j->build_rows : 1) * 4));
+    if (s.build_outer) {
+        GSQL_TRY(j->used.alloc(ctx, (size_t)(j->build_rows > 0 ? j->build_rows : 1)));
+        GSQL_CUDA(ctx, cudaMemsetAsync(j->used.p, 0, j->used.bytes, ctx->stream));
+    }
+    {
+        KernelScope ks(ctx, "join_slots_init");
+        k_slots_init<<<grid_rows(ctx, (int64_t)j->nslots + 1, 256, 8), 256, 0, ctx->stream>>>(j->slots.as<Slot>(), j->nslots + 1);
+    }
+    if (j->build_rows > 0) {
+        DColSet build;
+        KeySet bkeys;
+        fill_build_cols(j, &build, &bkeys);
+        KernelScope ks(ctx, "join_build");
+        k_join_build<<<grid_rows(ctx, j->build_rows, 256, 8), 256, 0, ctx->stream>>>(bkeys, j->build_rows, j->slots.as<Slot>(), j->nslots,
+                                                                                        j->links.as<int32_t>(), j->flags.as<int32_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    int32_t hflags[F_COUNT];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hflags, j->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    j->any_multi = hflags[F_ANY_MULTI] != 0;
+    j->built = true;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_join_info_get(gsql_join *j, gsql_join_info *info) {
+    if (!j || !info) return GSQL_E_INVALID;
+    memset(info, 0, sizeof(*info));
+    info->build_rows = j->build_rows;
+    info->table_slots = (int64_t)j->nslots;
+    info->table_bytes = (int64_t)j->slots.bytes;
+    int64_t tot = (int64_t)(j->slots.bytes + j->links.bytes + j->used.bytes);
+    for (int i = 0; i < j->n_build; i++) tot += (int64_t)(j->bdata[i].bytes + j->bnulls[i].bytes);
+    info->device_bytes = tot;
+    info->has_duplicate_keys = j->any_multi;
+    info->pass_through = j->pass_through;
+    info->pass_nothing = j->pass_nothing;
+    info->fast_path = 0;
+    info->partitions = 1;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_join_output_schema(gsql_join *j, int32_t *ncols, int32_t *types) {
+    if (!j || !ncols) return GSQL_E_INVALID;
+    *ncols = j->nout;
+    if (types)
+        for (int i = 0; i < j->nout; i++) types[i] = j->out_types[i];
+    return GSQL_OK;
+}
+
+namespace {
+
+// Everything a probe call holds in HBM besides the table.
+struct ProbeWork {
+    StagedBatch probe;
+    DevBuf cnt, off, scan_tmp, total;
+    DevBuf out_data[GSQL_MAX_COLS * 2], out_nulls[GSQL_MAX_COLS * 2];
+};
+
+gsql_status fill_params(gsql_join *j, const StagedBatch &sp, ProbeParams *P) {
+    memset(P, 0, sizeof(*P));
+    const gsql_join_spec &s = j->spec;
+    fill_build_cols(j, &P->build, &P->bkeys);
+    P->probe.n = sp.ncols;
+    for (int i = 0; i < sp.ncols; i++) P->probe.c[i] = sp.cols[i];
+    P->pkeys.n = s.nkeys;
+    for (int i = 0; i < s.nkeys; i++) {
+        P->pkeys.c[i] = sp.cols[j->pkey_cols[i]];
+        P->pkeys.utype[i] = s.key_type[i];
+    }
+    P->slots = j->slots.as<Slot>();
+    P->links = j->links.as<int32_t>();
+    P->used = j->used.as<uint8_t>();
+    P->flags = j->flags.as<int32_t>();
+    P->nslots = j->nslots;
+    P->probe_rows = sp.rows;
+    P->join_type = s.join_type;
+    P->single_join = j->single_join;
+    P->semi_join = j->semi_join;
+    P->outer_join = j->outer_join;
+    P->build_outer = s.build_outer;
+    P->exact = s.nkeys == 1;
+    P->n_anti = s.n_anti_operands;
+    for (int i = 0; i < s.n_anti_operands; i++) P->anti_cols[i] = s.anti_operands[i];
+    P->n_cond = s.n_cond;
+    for (int i = 0; i < s.n_cond; i++) {
+        P->cond_side[i] = j->cond_side[i];
+        P->cond_col[i] = j->cond_col[i];
+        P->cond_ne[i] = s.cond_ne_value[i];
+    }
+    P->nout = j->nout;
+    for (int q = 0; q < j->nout; q++) {
+        P->out[q].type = j->out_types[q];
+        P->out[q].side = j->out_side[q];
+        P->out[q].col = j->out_col[q];
+    }
+    return GSQL_OK;
+}
+
+// count kernel + exclusive scan; leaves per-row offsets in w->off and returns the total.
+gsql_status count_and_scan(gsql_join *j, const ProbeParams &P, int64_t rows, bool unmatched, ProbeWork *w, int64_t *total) {
+    gsql_ctx *ctx = j->ctx;
+    *total = 0;
+    if (rows == 0) return GSQL_OK;
+    GSQL_TRY(w->cnt.alloc(ctx, (size_t)rows * 4));
+    GSQL_TRY(w->off.alloc(ctx, (size_t)(rows + 1) * 8));
+    GSQL_TRY(w->total.alloc(ctx, 16));
+    if (unmatched) {
+        KernelScope ks(ctx, "join_unmatched_count");
+        k_unmatched_count<<<grid_rows(ctx, rows, 256, 8), 256, 0, ctx->stream>>>(j->used.as<uint8_t>(), rows, w->cnt.as<int32_t>());
+    } else {
+        KernelScope ks(ctx, "join_probe_count");
+        k_probe_count<<<grid_rows(ctx, rows, 256, 8), 256, 0, ctx->stream>>>(P, w->cnt.as<int32_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    cub::TransformInputIterator<int64_t, ToI64, const int32_t *> in(w->cnt.as<int32_t>(), ToI64());
+    size_t tmp = 0;
+    GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, w->off.as<int64_t>(), rows, ctx->stream));
+    GSQL_TRY(w->scan_tmp.alloc(ctx, tmp));
+    {
+        KernelScope ks(ctx, "join_scan");
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(w->scan_tmp.p, tmp, in, w->off.as<int64_t>(), rows, ctx->stream));
+    }
+    int64_t last_off = 0;
+    int32_t last_cnt = 0;
+    GSQL_CUDA(ctx, cudaMemcpyAsync(&last_off, w->off.as<int64_t>() + (rows - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(&last_cnt, w->cnt.as<int32_t>() + (rows - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *total = last_off + last_cnt;
+    return GSQL_OK;
+}
+
+gsql_status check_flags(gsql_join *j) {
+    gsql_ctx *ctx = j->ctx;
+    int32_t hflags[F_COUNT];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hflags, j->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hflags[F_MORE_THAN_ONE]) {
+        int32_t zero = 0;
+        cudaMemcpyAsync(j->flags.as<int32_t>() + F_MORE_THAN_ONE, &zero, 4, cudaMemcpyHostToDevice, ctx->stream);
+        return gsql_set_error(ctx, GSQL_E_MORE_THAN_ONE_ROW, "ERR_SCALAR_SUBQUERY_RETURN_MORE_THAN_ONE_ROW");
+    }
+    if (hflags[F_NULL_INTO_NONNULL]) {
+        int32_t zero = 0;
+        cudaMemcpyAsync(j->flags.as<int32_t>() + F_NULL_INTO_NONNULL, &zero, 4, cudaMemcpyHostToDevice, ctx->stream);
+        return gsql_set_error(ctx, GSQL_E_INVALID, "a NULL had to be written into an output column without a nulls buffer");
+    }
+    return GSQL_OK;
+}
+
+// Binds caller output columns (device) or temp device columns (host batch) into P->out.
+gsql_status bind_outputs(gsql_join *j, gsql_batch *out, int64_t rows, ProbeParams *P, ProbeWork *w) {
+    gsql_ctx *ctx = j->ctx;
+    for (int q = 0; q < j->nout; q++) {
+        if (out->mem == GSQL_MEM_DEVICE) {
+            P->out[q].data = out->cols[q].data;
+            P->out[q].nulls = out->cols[q].nulls;
+        } else {
+            GSQL_TRY(w->out_data[q].alloc(ctx, (size_t)rows * gsql_type_width(j->out_types[q])));
+            P->out[q].data = w->out_data[q].p;
+            P->out[q].nulls = nullptr;
+            if (out->cols[q].nulls) {
+                GSQL_TRY(w->out_nulls[q].alloc(ctx, (size_t)rows));
+                P->out[q].nulls = w->out_nulls[q].as<uint8_t>();
+            }
+        }
+    }
+    return GSQL_OK;
+}
+
+gsql_status download_outputs(gsql_join *j, gsql_batch *out, int64_t rows, const ProbeParams &P) {
+    gsql_ctx *ctx = j->ctx;
+    if (out->mem == GSQL_MEM_DEVICE || rows == 0) return GSQL_OK;
+    for (int q = 0; q < j->nout; q++) {
+        GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[q].data, P.out[q].data, (size_t)rows * gsql_type_width(j->out_types[q]), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out->cols[q].nulls) GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[q].nulls, P.out[q].nulls, (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return GSQL_OK;
+}
+
+}  // namespace
+
+extern "C" gsql_status gsql_join_probe_count(gsql_join *j, const gsql_batch *probe, int64_t *out_rows) {
+    if (!j || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (!j->built) return gsql_set_error(ctx, GSQL_E_STATE, "probe before build_finish");
+    GSQL_TRY(validate_batch(ctx, probe, j->n_probe, j->probe_types));
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    *out_rows = 0;
+    if (j->pass_nothing) return GSQL_OK;
+    if (j->pass_through) { *out_rows = probe->rows; return GSQL_OK; }
+    if (probe->rows == 0) return GSQL_OK;
+    ProbeWork w;
+    GSQL_TRY(stage_batch(ctx, probe, &w.probe));
+    ProbeParams P;
+    GSQL_TRY(fill_params(j, w.probe, &P));
+    GSQL_TRY(count_and_scan(j, P, probe->rows, false, &w, out_rows));
+    return check_flags(j);
+}
+
+extern "C" gsql_status gsql_join_probe(gsql_join *j, const gsql_batch *probe, gsql_batch *out, int64_t out_capacity, int64_t *out_rows) {
+    if (!j || !out || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (!j->built) return gsql_set_error(ctx, GSQL_E_STATE, "probe before build_finish");
+    GSQL_TRY(validate_batch(ctx, probe, j->n_probe, j->probe_types));
+    GSQL_TRY(validate_batch(ctx, out, j->nout, j->out_types));
+    if (out->mem != probe->mem) return gsql_set_error(ctx, GSQL_E_INVALID, "probe and out must live in the same memory space");
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    *out_rows = 0;
+    out->rows = 0;
+    if (j->pass_nothing || probe->rows == 0) return GSQL_OK;
+    if (j->pass_through) {  // ANTI with an empty build side: every probe row passes (even NULL operands)
+        if (out_capacity < probe->rows) { *out_rows = probe->rows; return gsql_set_error(ctx, GSQL_E_CAPACITY, "need %lld rows", (long long)probe->rows); }
+        cudaMemcpyKind kind = probe->mem == GSQL_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToHost;
+        for (int q = 0; q < j->nout; q++) {
+            const gsql_col &src = probe->cols[j->out_col[q]];
+            GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[q].data, src.data, (size_t)probe->rows * gsql_type_width(src.type), kind, ctx->stream));
+            if (src.nulls) {
+                if (!out->cols[q].nulls) return gsql_set_error(ctx, GSQL_E_INVALID, "output column %d needs a nulls buffer", q);
+                GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[q].nulls, src.nulls, (size_t)probe->rows, kind, ctx->stream));
+            } else if (out->cols[q].nulls) {
+                if (probe->mem == GSQL_MEM_DEVICE) GSQL_CUDA(ctx, cudaMemsetAsync(out->cols[q].nulls, 0, (size_t)probe->rows, ctx->stream));
+                else memset(out->cols[q].nulls, 0, (size_t)probe->rows);
+            }
+        }
+        GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *out_rows = out->rows = probe->rows;
+        return GSQL_OK;
+    }
+    ProbeWork w;
+    GSQL_TRY(stage_batch(ctx, probe, &w.probe));
+    ProbeParams P;
+    GSQL_TRY(fill_params(j, w.probe, &P));
+    int64_t total = 0;
+    GSQL_TRY(count_and_scan(j, P, probe->rows, false, &w, &total));
+    GSQL_TRY(check_flags(j));
+    if (total > out_capacity) {
+        *out_rows = total;
+        return gsql_set_error(ctx, GSQL_E_CAPACITY, "output needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
+    }
+    if (total > 0) {
+        GSQL_TRY(bind_outputs(j, out, total, &P, &w));
+        {
+            KernelScope ks(ctx, "join_probe_write");
+            k_probe_write<<<grid_rows(ctx, probe->rows, 256, 8), 256, 0, ctx->stream>>>(P, w.off.as<int64_t>());
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+        GSQL_TRY(check_flags(j));
+        GSQL_TRY(download_outputs(j, out, total, P));
+    }
+    *out_rows = out->rows = total;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_join_unmatched_build(gsql_join *j, gsql_batch *out, int64_t out_capacity, int64_t *out_rows) {
+    if (!j || !out || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (!j->built) return gsql_set_error(ctx, GSQL_E_STATE, "unmatched_build before build_finish");
+    GSQL_TRY(validate_batch(ctx, out, j->nout, j->out_types));
+    *out_rows = 0;
+    out->rows = 0;
+    if (!j->spec.build_outer || !j->outer_join || j->build_rows == 0) return GSQL_OK;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    ProbeWork w;
+    w.probe.rows = 0;
+    w.probe.ncols = j->n_probe;
+    for (int i = 0; i < j->n_probe; i++) w.probe.cols[i] = DCol{nullptr, nullptr, j->probe_types[i], 0};
+    ProbeParams P;
+    GSQL_TRY(fill_params(j, w.probe, &P));
+    int64_t total = 0;
+    GSQL_TRY(count_and_scan(j, P, j->build_rows, true, &w, &total));
+    if (total > out_capacity) {
+        *out_rows = total;
+        return gsql_set_error(ctx, GSQL_E_CAPACITY, "output needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
+    }
+    if (total > 0) {
+        GSQL_TRY(bind_outputs(j, out, total, &P, &w));
+        {
+            KernelScope ks(ctx, "join_unmatched_write");
+            k_unmatched_write<<<grid_rows(ctx, j->build_rows, 256, 8), 256, 0, ctx->stream>>>(P, j->build_rows, w.off.as<int64_t>());
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+        GSQL_TRY(check_flags(j));
+        GSQL_TRY(download_outputs(j, out, total, P));
+    }
+    *out_rows = out->rows = total;
+    return GSQL_OK;
+}

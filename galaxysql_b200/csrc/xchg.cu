@@ -1,0 +1,384 @@
+// xchg.cu — hash-partition exchange behind gsql_xchg_* and gsql_comm_*.
+//
+// Reference path replaced (EX/ = polardbx-executor/src/main/java/com/alibaba/polardbx/executor/):
+//   local : EX/mpp/operator/PartitioningExchanger.java:71-135 (consumeChunk: per-row partition id, per-destination
+//           chunk build), HashBucketFunction (PartitionedOutputCollector.java:282-302)
+//   remote: EX/mpp/operator/PartitionedOutputCollector.java:170-196 (partitionPage) + HashPartitionFunction:253-279,
+//           PagesSerde / PartitionedOutputBuffer / ExchangeClient HTTP pull (ExchangeClient.java:62-548)
+// Destination ids are bit-exact with ExecUtils.partition(Chunk.hashCode) so GPU and stock Java tasks route the
+// same row to the same consumer.
+//
+// B200 shape: histogram (keys only) -> exclusive scan over [partition][block] -> scatter of all columns into one
+// buffer whose partitions are contiguous; across GPUs the contiguous segments are exchanged with one grouped
+// ncclSend/ncclRecv AllToAllv per column over NVLink 5 / NVSwitch — no serialisation, no compression.
+// NCCL is bound at run time (dlopen) so that the library shares the process's NCCL with torch.distributed.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cub/device/device_scan.cuh>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int XBLOCK = 256;
+
+struct XParams {
+    DColSet in;
+    KeySet keys;
+    int32_t nparts, pow2;
+    int64_t rows, chunk;  // rows per block
+    int32_t nblocks, pad;
+};
+
+struct XOut {
+    void *data[GSQL_MAX_COLS];
+    uint8_t *nulls[GSQL_MAX_COLS];
+};
+
+__device__ __forceinline__ int row_part(const XParams &P, int64_t r) {
+    return gsql_partition_of(gsql_row_hash(P.keys, r), P.nparts, P.pow2 != 0);
+}
+
+// hist[p * nblocks + b] = rows of block b's chunk routed to p
+__global__ void __launch_bounds__(XBLOCK) k_xchg_hist(const __grid_constant__ XParams P, int64_t *__restrict__ hist) {
+    extern __shared__ unsigned int sh[];
+    for (int i = threadIdx.x; i < P.nparts; i += XBLOCK) sh[i] = 0;
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * P.chunk;
+    int64_t r1 = r0 + P.chunk < P.rows ? r0 + P.chunk : P.rows;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += XBLOCK) atomicAdd(&sh[row_part(P, r)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < P.nparts; i += XBLOCK) hist[(int64_t)i * P.nblocks + blockIdx.x] = sh[i];
+}
+
+__global__ void __launch_bounds__(XBLOCK)
+    k_xchg_scatter(const __grid_constant__ XParams P, const int64_t *__restrict__ offs, const __grid_constant__ XOut O) {
+    extern __shared__ unsigned long long cur[];
+    for (int i = threadIdx.x; i < P.nparts; i += XBLOCK) cur[i] = (unsigned long long)offs[(int64_t)i * P.nblocks + blockIdx.x];
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * P.chunk;
+    int64_t r1 = r0 + P.chunk < P.rows ? r0 + P.chunk : P.rows;
+    for (int64_t base = r0; base < r1; base += XBLOCK) {
+        int64_t r = base + threadIdx.x;
+        bool live = r < r1;
+        int p = live ? row_part(P, r) : -1;
+        // warp-aggregated cursor bump: one shared-memory atomic per distinct destination per warp
+        unsigned peers = __match_any_sync(0xffffffffu, p);
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(peers) - 1;
+        unsigned long long basepos = 0;
+        if (live && lane == leader) basepos = atomicAdd(&cur[p], (unsigned long long)__popc(peers));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (!live) continue;
+        int64_t pos = (int64_t)basepos + __popc(peers & ((1u << lane) - 1));
+        for (int c = 0; c < P.in.n; c++) {
+            const DCol &col = P.in.c[c];
+            if (col.type == GSQL_T_INT32) reinterpret_cast<int32_t *>(O.data[c])[pos] = reinterpret_cast<const int32_t *>(col.data)[r];
+            else reinterpret_cast<int64_t *>(O.data[c])[pos] = reinterpret_cast<const int64_t *>(col.data)[r];
+            if (O.nulls[c]) O.nulls[c][pos] = col.nulls ? col.nulls[r] : 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ NCCL binding
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi *nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return &api;
+    tried = true;
+    // Prefer the NCCL already in the process (torch's bundled one), else the system library.
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return &api;
+    api.handle = h;
+#define BIND(field, sym) *(void **)(&api.field) = dlsym(h, sym)
+    BIND(GetUniqueId, "ncclGetUniqueId");
+    BIND(CommInitRank, "ncclCommInitRank");
+    BIND(CommDestroy, "ncclCommDestroy");
+    BIND(AllGather, "ncclAllGather");
+    BIND(Send, "ncclSend");
+    BIND(Recv, "ncclRecv");
+    BIND(GroupStart, "ncclGroupStart");
+    BIND(GroupEnd, "ncclGroupEnd");
+    BIND(GetErrorString, "ncclGetErrorString");
+#undef BIND
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Send && api.Recv && api.GroupStart &&
+             api.GroupEnd && api.GetErrorString;
+    return &api;
+}
+
+#define GSQL_NCCL(ctx, call)                                                                                            \
+    do {                                                                                                                \
+        ncclResult_t _r = (call);                                                                                       \
+        if (_r != ncclSuccess) {                                                                                        \
+            (ctx)->sticky = true;                                                                                       \
+            return gsql_set_error((ctx), GSQL_E_NCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, nccl_api()->GetErrorString(_r)); \
+        }                                                                                                               \
+    } while (0)
+
+int grid_rows(gsql_ctx *ctx, int64_t rows, int block, int per_sm) {
+    int64_t g = div_up(rows, block);
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace
+
+struct gsql_xchg {
+    gsql_ctx *ctx;
+    gsql_xchg_spec spec;
+};
+
+extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spec, gsql_xchg **out) {
+    if (!ctx || !spec || !out) return GSQL_E_INVALID;
+    *out = nullptr;
+    const gsql_xchg_spec &s = *spec;
+    if (s.n_cols < 1 || s.n_cols > GSQL_MAX_COLS || s.n_channels < 0 || s.n_channels > GSQL_MAX_KEYS || s.nparts < 1 || s.nparts > GSQL_MAX_PARTS)
+        return gsql_set_error(ctx, GSQL_E_INVALID, "bad exchange spec");
+    for (int i = 0; i < s.n_cols; i++)
+        if (s.types[i] < GSQL_T_INT32 || s.types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "column %d type", i);
+    for (int i = 0; i < s.n_channels; i++)
+        if (s.channels[i] < 0 || s.channels[i] >= s.n_cols || s.key_types[i] < GSQL_T_INT32 || s.key_types[i] > GSQL_T_FP64)
+            return gsql_set_error(ctx, GSQL_E_INVALID, "channel %d", i);
+    gsql_xchg *x = new gsql_xchg();
+    x->ctx = ctx;
+    x->spec = s;
+    *out = x;
+    return GSQL_OK;
+}
+
+extern "C" void gsql_xchg_destroy(gsql_xchg *x) { delete x; }
+
+// Partitions staged device columns into `O` (device).  d_part_offsets receives nparts+1 int64 offsets (device).
+static gsql_status partition_device(gsql_xchg *x, const StagedBatch &sb, const XOut &O, DevBuf *offs_out, int64_t *host_counts) {
+    gsql_ctx *ctx = x->ctx;
+    const gsql_xchg_spec &s = x->spec;
+    XParams P;
+    memset(&P, 0, sizeof(P));
+    P.in.n = sb.ncols;
+    for (int i = 0; i < sb.ncols; i++) P.in.c[i] = sb.cols[i];
+    P.keys.n = s.n_channels;
+    for (int i = 0; i < s.n_channels; i++) {
+        P.keys.c[i] = sb.cols[s.channels[i]];
+        P.keys.utype[i] = s.key_types[i];
+    }
+    P.nparts = s.nparts;
+    P.pow2 = (s.nparts & -s.nparts) == s.nparts;
+    P.rows = sb.rows;
+    int nblocks = grid_rows(ctx, sb.rows, 4096, 8);
+    P.chunk = div_up(sb.rows, nblocks);
+    P.chunk = div_up(P.chunk, XBLOCK) * XBLOCK;
+    nblocks = (int)div_up(sb.rows, P.chunk);
+    if (nblocks < 1) nblocks = 1;
+    P.nblocks = nblocks;
+    int64_t nh = (int64_t)s.nparts * nblocks;
+    DevBuf hist, tmp;
+    GSQL_TRY(hist.alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_TRY(offs_out->alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_CUDA(ctx, cudaMemsetAsync((char *)hist.p + nh * 8, 0, 8, ctx->stream));
+    {
+        KernelScope ks(ctx, "xchg_hist");
+        k_xchg_hist<<<nblocks, XBLOCK, s.nparts * sizeof(unsigned int), ctx->stream>>>(P, hist.as<int64_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    size_t tb = 0;
+    GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist.as<int64_t>(), offs_out->as<int64_t>(), nh + 1, ctx->stream));
+    GSQL_TRY(tmp.alloc(ctx, tb));
+    {
+        KernelScope ks(ctx, "xchg_scan");
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist.as<int64_t>(), offs_out->as<int64_t>(), nh + 1, ctx->stream));
+    }
+    {
+        KernelScope ks(ctx, "xchg_scatter");
+        k_xchg_scatter<<<nblocks, XBLOCK, s.nparts * sizeof(unsigned long long), ctx->stream>>>(P, offs_out->as<int64_t>(), O);
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    if (host_counts) {  // partition p starts at offs[p * nblocks]
+        std::vector<int64_t> starts((size_t)s.nparts + 1);
+        GSQL_CUDA(ctx, cudaMemcpy2DAsync(starts.data(), 8, offs_out->p, (size_t)nblocks * 8, 8, (size_t)s.nparts, cudaMemcpyDeviceToHost, ctx->stream));
+        GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        starts[(size_t)s.nparts] = sb.rows;
+        for (int p = 0; p < s.nparts; p++) host_counts[p] = starts[(size_t)p + 1] - starts[(size_t)p];
+    }
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_xchg_partition(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t *part_counts) {
+    if (!x || !in || !out || !part_counts) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    const gsql_xchg_spec &s = x->spec;
+    GSQL_TRY(validate_batch(ctx, in, s.n_cols, s.types));
+    GSQL_TRY(validate_batch(ctx, out, s.n_cols, s.types));
+    if (in->mem != out->mem) return gsql_set_error(ctx, GSQL_E_INVALID, "in and out must live in the same memory space");
+    for (int p = 0; p < s.nparts; p++) part_counts[p] = 0;
+    out->rows = in->rows;
+    if (in->rows == 0) return GSQL_OK;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int c = 0; c < s.n_cols; c++)
+        if (in->cols[c].nulls && !out->cols[c].nulls) return gsql_set_error(ctx, GSQL_E_INVALID, "output column %d needs a nulls buffer", c);
+    StagedBatch sb;
+    GSQL_TRY(stage_batch(ctx, in, &sb));
+    XOut O;
+    memset(&O, 0, sizeof(O));
+    DevBuf odata[GSQL_MAX_COLS], onull[GSQL_MAX_COLS];
+    for (int c = 0; c < s.n_cols; c++) {
+        if (in->mem == GSQL_MEM_DEVICE) {
+            O.data[c] = out->cols[c].data;
+            O.nulls[c] = out->cols[c].nulls;
+        } else {
+            GSQL_TRY(odata[c].alloc(ctx, (size_t)in->rows * gsql_type_width(s.types[c])));
+            O.data[c] = odata[c].p;
+            if (out->cols[c].nulls) {
+                GSQL_TRY(onull[c].alloc(ctx, (size_t)in->rows));
+                O.nulls[c] = onull[c].as<uint8_t>();
+            }
+        }
+    }
+    DevBuf offs;
+    GSQL_TRY(partition_device(x, sb, O, &offs, part_counts));
+    if (in->mem == GSQL_MEM_HOST) {
+        for (int c = 0; c < s.n_cols; c++) {
+            GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[c].data, O.data[c], (size_t)in->rows * gsql_type_width(s.types[c]), cudaMemcpyDeviceToHost, ctx->stream));
+            if (out->cols[c].nulls) GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[c].nulls, O.nulls[c], (size_t)in->rows, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return GSQL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ communicator
+extern "C" gsql_status gsql_comm_unique_id(uint8_t id[128]) {
+    NcclApi *api = nccl_api();
+    if (!api->ok || !id) return GSQL_E_NCCL;
+    ncclUniqueId uid;
+    if (api->GetUniqueId(&uid) != ncclSuccess) return GSQL_E_NCCL;
+    memcpy(id, uid.internal, 128);
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_comm_init(gsql_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t id[128]) {
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return GSQL_E_INVALID;
+    NcclApi *api = nccl_api();
+    if (!api->ok) return gsql_set_error(ctx, GSQL_E_NCCL, "libnccl.so.2 could not be loaded");
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    ncclComm_t comm;
+    GSQL_NCCL(ctx, api->CommInitRank(&comm, nranks, uid, rank));
+    ctx->nccl_comm = comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_comm_destroy(gsql_ctx *ctx) {
+    if (!ctx) return GSQL_E_INVALID;
+    if (ctx->nccl_comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm);
+        ctx->nccl_comm = nullptr;
+    }
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t out_capacity,
+                                            int64_t *out_rows, int64_t *recv_counts) {
+    if (!x || !in || !out || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    const gsql_xchg_spec &s = x->spec;
+    NcclApi *api = nccl_api();
+    if (!ctx->nccl_comm || !api->ok) return gsql_set_error(ctx, GSQL_E_STATE, "gsql_comm_init has not been called");
+    if (s.nparts != ctx->nranks) return gsql_set_error(ctx, GSQL_E_INVALID, "exchange has %d partitions but the communicator has %d ranks", s.nparts, ctx->nranks);
+    GSQL_TRY(validate_batch(ctx, in, s.n_cols, s.types));
+    GSQL_TRY(validate_batch(ctx, out, s.n_cols, s.types));
+    if (in->mem != GSQL_MEM_DEVICE || out->mem != GSQL_MEM_DEVICE) return gsql_set_error(ctx, GSQL_E_INVALID, "all_to_all works on device-resident batches");
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int R = ctx->nranks;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    // nullable columns must be nullable on every rank (collective shape): decided by the output buffers
+    // ---- 1. partition into contiguous per-destination segments
+    StagedBatch sb;
+    GSQL_TRY(stage_batch(ctx, in, &sb));
+    XOut O;
+    memset(&O, 0, sizeof(O));
+    DevBuf sdata[GSQL_MAX_COLS], snull[GSQL_MAX_COLS];
+    int64_t srows = in->rows > 0 ? in->rows : 1;
+    for (int c = 0; c < s.n_cols; c++) {
+        GSQL_TRY(sdata[c].alloc(ctx, (size_t)srows * gsql_type_width(s.types[c])));
+        O.data[c] = sdata[c].p;
+        if (out->cols[c].nulls) {
+            GSQL_TRY(snull[c].alloc(ctx, (size_t)srows));
+            O.nulls[c] = snull[c].as<uint8_t>();
+        }
+    }
+    std::vector<int64_t> send_counts((size_t)R, 0);
+    DevBuf offs;
+    if (in->rows > 0) GSQL_TRY(partition_device(x, sb, O, &offs, send_counts.data()));
+    // ---- 2. exchange the R x R count matrix
+    DevBuf d_counts, d_matrix;
+    GSQL_TRY(d_counts.alloc(ctx, (size_t)R * 8));
+    GSQL_TRY(d_matrix.alloc(ctx, (size_t)R * R * 8));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(d_counts.p, send_counts.data(), (size_t)R * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GSQL_NCCL(ctx, api->AllGather(d_counts.p, d_matrix.p, (size_t)R, ncclInt64, comm, ctx->stream));
+    std::vector<int64_t> matrix((size_t)R * R);
+    GSQL_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)R * R * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int64_t total = 0;
+    std::vector<int64_t> roff((size_t)R), soff((size_t)R);
+    for (int src = 0; src < R; src++) {
+        roff[(size_t)src] = total;
+        int64_t n = matrix[(size_t)src * R + ctx->rank];
+        if (recv_counts) recv_counts[src] = n;
+        total += n;
+    }
+    int64_t acc = 0;
+    for (int dst = 0; dst < R; dst++) {
+        soff[(size_t)dst] = acc;
+        acc += send_counts[(size_t)dst];
+    }
+    *out_rows = total;
+    // capacity must be judged identically by all ranks or the collective below would hang: every rank can see the
+    // whole matrix, so all of them learn whether anyone overflows... each rank has its own capacity, so the caller
+    // contract is: size `out` for the worst case (sum over sources) or retry collectively.
+    if (total > out_capacity) return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
+    // ---- 3. AllToAllv: one grouped send/recv per column (and per null mask)
+    {
+        KernelScope ks(ctx, "xchg_alltoall");
+        GSQL_NCCL(ctx, api->GroupStart());
+        for (int c = 0; c < s.n_cols; c++) {
+            size_t w = (size_t)gsql_type_width(s.types[c]);
+            for (int peer = 0; peer < R; peer++) {
+                int64_t ns = send_counts[(size_t)peer], nr = matrix[(size_t)peer * R + ctx->rank];
+                if (ns > 0) GSQL_NCCL(ctx, api->Send((char *)sdata[c].p + (size_t)soff[(size_t)peer] * w, (size_t)ns * w, ncclInt8, peer, comm, ctx->stream));
+                if (nr > 0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].data + (size_t)roff[(size_t)peer] * w, (size_t)nr * w, ncclInt8, peer, comm, ctx->stream));
+                if (out->cols[c].nulls) {
+                    if (ns > 0) GSQL_NCCL(ctx, api->Send((char *)snull[c].p + soff[(size_t)peer], (size_t)ns, ncclInt8, peer, comm, ctx->stream));
+                    if (nr > 0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].nulls + roff[(size_t)peer], (size_t)nr, ncclInt8, peer, comm, ctx->stream));
+                }
+            }
+        }
+        GSQL_NCCL(ctx, api->GroupEnd());
+    }
+    out->rows = total;
+    return GSQL_OK;
+}

@@ -1,0 +1,261 @@
+/*
+ * gsql_gpu.h — C ABI of the B200-native MPP operator hot path for GalaxySQL (PolarDB-X CN).
+ *
+ * This is the drop-in boundary: exactly the entry points a JNI shim under
+ * com.alibaba.polardbx.executor.operator.Gpu*Exec would bind (INTEGRATION.md shows the Java/JNI side).
+ * Plain pointers and sizes only; no CUDA, torch or C++ types in any signature.
+ *
+ * Reference interfaces replaced (paths relative to
+ * polardbx-executor/src/main/java/com/alibaba/polardbx/executor/):
+ *   gsql_batch / gsql_col        <- chunk/Chunk.java:41-100, chunk/Block.java:33, chunk/AbstractBlock.java:27-47
+ *                                   (IntegerBlock.java:37 int[], LongBlock.java:41 long[], DoubleBlock.java:33 double[],
+ *                                    boolean[] isNull -> one byte per row)
+ *   gsql_hash_rows               <- chunk/Chunk.java:116-130 (hashCodeVector / hashCode)
+ *   gsql_partition_ids           <- utils/ExecUtils.java:1023-1031 (partition)
+ *   gsql_join_*                  <- operator/ParallelHashJoinExec.java:64-85 (ctor), :157-166 (consumeChunk),
+ *                                   :107-128 (buildConsume), operator/AbstractBufferedJoinExec.java:116-264
+ *                                   (doNextChunk / nextRows), :168-201 (nextJoinNullRows)
+ *   gsql_agg_*                   <- operator/HashAggExec.java:74-91 (ctor), :133-145 (consumeChunk), :158-162
+ *                                   (buildConsume), operator/AbstractHashAggExec.java:57-63 (doNextChunk)
+ *   gsql_xchg_*                  <- mpp/operator/PartitioningExchanger.java:71-135 (local exchange),
+ *                                   mpp/operator/PartitionedOutputCollector.java:170-196 + ExchangeClient.java:62-548
+ *                                   (remote shuffle; replaced by an NCCL AllToAllv over NVLink)
+ *
+ * Threading: every handle is thread-compatible (the caller serialises calls on one handle, as the reference's
+ * Driver does — mpp/operator/Driver.java:449-508); distinct handles may be used from distinct threads.
+ * Errors: every call returns a gsql_status; gsql_last_error(ctx) gives the message.  CUDA/NCCL errors are sticky
+ * per context.  *_destroy never fails and accepts NULL.
+ * There is NO CPU fallback anywhere behind this ABI: without a CUDA device gsql_ctx_create fails with GSQL_E_CUDA.
+ */
+#ifndef GSQL_GPU_H
+#define GSQL_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
+
+#define GSQL_ABI_VERSION 1
+#define GSQL_MAX_KEYS 8
+#define GSQL_MAX_COLS 32
+#define GSQL_MAX_AGGS 16
+#define GSQL_MAX_PARTS 1024
+
+typedef enum gsql_status {
+    GSQL_OK = 0,
+    GSQL_E_INVALID = 1,           /* bad argument / unsupported combination (planner must fall through) */
+    GSQL_E_CUDA = 2,
+    GSQL_E_NCCL = 3,
+    GSQL_E_CAPACITY = 4,          /* output buffer too small; *out_rows holds the required row count */
+    GSQL_E_MORE_THAN_ONE_ROW = 5, /* ErrorCode.ERR_SCALAR_SUBQUERY_RETURN_MORE_THAN_ONE_ROW */
+    GSQL_E_UNSUPPORTED = 6,
+    GSQL_E_STATE = 7,             /* call order violated (e.g. probe before build_finish) */
+    GSQL_E_OOM = 8
+} gsql_status;
+
+typedef enum gsql_type {
+    GSQL_T_INT32 = 0,  /* IntegerBlock */
+    GSQL_T_INT64 = 1,  /* LongBlock    */
+    GSQL_T_FP64 = 2,   /* DoubleBlock  */
+    GSQL_T_DEC128 = 3  /* output only: exact SUM(int|bigint) as a little-endian two's-complement int128, scale 0
+                          (stands for the DECIMAL of LittleNum2DecimalSum.java:45-82) */
+} gsql_type;
+
+typedef enum gsql_mem { GSQL_MEM_HOST = 0, GSQL_MEM_DEVICE = 1 } gsql_mem;
+
+typedef enum gsql_join_type {
+    GSQL_JOIN_INNER = 0, GSQL_JOIN_LEFT = 1, GSQL_JOIN_RIGHT = 2, GSQL_JOIN_SEMI = 3, GSQL_JOIN_ANTI = 4
+} gsql_join_type;
+
+typedef enum gsql_agg_kind {
+    GSQL_AGG_COUNT_STAR = 0, /* CountRow */
+    GSQL_AGG_COUNT = 1,      /* Count: all listed columns non-NULL */
+    GSQL_AGG_SUM = 2,        /* FP64 -> FP64 (Double2DoubleSum); INT32/INT64 -> DEC128 (Int/Long2DecimalSum) */
+    GSQL_AGG_AVG = 3,        /* FP64 -> FP64 (Double2DoubleAvg) */
+    GSQL_AGG_MIN = 4,
+    GSQL_AGG_MAX = 5,
+    GSQL_AGG_SUM0 = 6        /* INT64 -> INT64 wrapping, never NULL (Long2LongSum0) */
+} gsql_agg_kind;
+
+/* One Block.  `nulls` == NULL means "no NULLs" (AbstractBlock.mayHaveNull() == false); otherwise one byte per
+ * row, non-zero = NULL, exactly the reference's boolean[] isNull. */
+typedef struct gsql_col {
+    int32_t type;     /* gsql_type */
+    int32_t reserved;
+    void *data;
+    uint8_t *nulls;
+} gsql_col;
+
+/* One Chunk (or many concatenated chunks: the GPU operators want large batches). All pointers of a batch live in
+ * the same memory space `mem`.  Host pointers should come from gsql_host_alloc (pinned) for full PCIe speed. */
+typedef struct gsql_batch {
+    int64_t rows;
+    int32_t ncols;
+    int32_t mem; /* gsql_mem */
+    gsql_col *cols;
+} gsql_batch;
+
+typedef struct gsql_ctx gsql_ctx;
+typedef struct gsql_join gsql_join;
+typedef struct gsql_agg gsql_agg;
+typedef struct gsql_xchg gsql_xchg;
+
+/* ------------------------------------------------------------------------------------------------ context */
+int gsql_abi_version(void);
+gsql_status gsql_ctx_create(int device, gsql_ctx **out);
+void gsql_ctx_destroy(gsql_ctx *ctx);
+const char *gsql_last_error(const gsql_ctx *ctx);
+gsql_status gsql_ctx_sync(gsql_ctx *ctx);
+/* The CUDA stream (cudaStream_t as void*) every kernel of this context is launched on; callers that keep data
+ * device-resident order their own work against it. */
+void *gsql_ctx_stream(gsql_ctx *ctx);
+gsql_status gsql_ctx_set_stream(gsql_ctx *ctx, void *cuda_stream);
+/* Per-kernel device timing (CUDA events on the launching stream).  Off by default. */
+gsql_status gsql_ctx_profile(gsql_ctx *ctx, int enable);
+gsql_status gsql_ctx_profile_reset(gsql_ctx *ctx);
+/* Returns launches and total milliseconds of kernel `name` since the last reset (synchronises the stream). */
+gsql_status gsql_ctx_profile_get(gsql_ctx *ctx, const char *name, int64_t *launches, double *total_ms);
+/* Writes up to `cap` bytes of "name launches ms\n" lines; returns the number of kernels recorded. */
+int gsql_ctx_profile_dump(gsql_ctx *ctx, char *buf, size_t cap);
+/* Total number of kernels this library launched on this context since creation. */
+int64_t gsql_ctx_launch_count(const gsql_ctx *ctx);
+
+gsql_status gsql_host_alloc(size_t bytes, void **out); /* pinned host memory */
+void gsql_host_free(void *p);
+gsql_status gsql_device_alloc(gsql_ctx *ctx, size_t bytes, void **out);
+void gsql_device_free(gsql_ctx *ctx, void *p);
+gsql_status gsql_memcpy_h2d(gsql_ctx *ctx, void *dst, const void *src, size_t bytes);
+gsql_status gsql_memcpy_d2h(gsql_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ------------------------------------------------------------------------------------------------ hashing */
+/* out[r] = Chunk.hashCode over key_cols[0..nkeys) converted to unified_types (NULL -> 0, h = h*31 + c).
+ * `out` lives in batch->mem.  Bit-exact with the reference (and with the oracle). */
+gsql_status gsql_hash_rows(gsql_ctx *ctx, const gsql_batch *batch, const int32_t *key_cols, int32_t nkeys,
+                           const int32_t *unified_types, int32_t *out);
+/* out[r] = ExecUtils.partition(hash[r], nparts).  `mem` says where hash/out live. */
+gsql_status gsql_partition_ids(gsql_ctx *ctx, const int32_t *hash, int64_t rows, int32_t nparts, int32_t *out,
+                               int32_t mem);
+
+/* ------------------------------------------------------------------------------------------------ hash join */
+typedef struct gsql_join_spec {
+    int32_t join_type;   /* gsql_join_type */
+    int32_t max_one_row; /* singleJoin: output = outer cols + first inner col; 2nd match is an error */
+    int32_t build_outer; /* buildOuterInput: the outer side is the build side */
+    int32_t nkeys;
+    int32_t outer_key[GSQL_MAX_KEYS]; /* EquiJoinKey.outerIndex */
+    int32_t inner_key[GSQL_MAX_KEYS]; /* EquiJoinKey.innerIndex */
+    int32_t key_type[GSQL_MAX_KEYS];  /* EquiJoinKey.unifiedType */
+    int32_t n_outer_cols;
+    int32_t outer_types[GSQL_MAX_COLS];
+    int32_t n_inner_cols;
+    int32_t inner_types[GSQL_MAX_COLS];
+    int32_t n_anti_operands;          /* 0 = antiJoinOperands == null (NOT EXISTS); else NOT IN null rules */
+    int32_t anti_operands[GSQL_MAX_KEYS];
+    /* otherCondition, restricted form: AND_i (joinRow[cond_col[i]] IS NULL OR joinRow[cond_col[i]] != cond_ne_value[i])
+     * over integer columns of the join row (leftSide || rightSide).  n_cond == 0 <=> otherCondition == null. */
+    int32_t n_cond;
+    int32_t cond_col[4];
+    int64_t cond_ne_value[4];
+    int64_t expected_build_rows; /* hint, 0 = unknown */
+} gsql_join_spec;
+
+typedef struct gsql_join_info {
+    int64_t build_rows;
+    int64_t table_slots;
+    int64_t table_bytes;
+    int64_t device_bytes; /* everything the handle holds in HBM */
+    int32_t has_duplicate_keys;
+    int32_t pass_through; /* 1: probe rows pass unchanged (ANTI with empty build) */
+    int32_t pass_nothing; /* 1: no output at all */
+    int32_t fast_path;    /* 1: single integer key specialisation active */
+    int32_t partitions;   /* >1: radix-partitioned (L2-resident) probe */
+    int32_t reserved;
+} gsql_join_info;
+
+gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spec, gsql_join **out);
+/* consumeChunk on the build side: appends (copies) the batch; nothing of `batch` is referenced after return. */
+gsql_status gsql_join_build_consume(gsql_join *j, const gsql_batch *build_rows);
+/* buildConsume: builds the hash table over everything consumed. */
+gsql_status gsql_join_build_finish(gsql_join *j);
+gsql_status gsql_join_info_get(gsql_join *j, gsql_join_info *info);
+/* Output schema (AbstractJoinExec.java:103-120). */
+gsql_status gsql_join_output_schema(gsql_join *j, int32_t *ncols, int32_t *types /* GSQL_MAX_COLS*2 */);
+/* Number of output rows `probe` would produce (exact). */
+gsql_status gsql_join_probe_count(gsql_join *j, const gsql_batch *probe, int64_t *out_rows);
+/* nextChunk over a probe batch.  `out` must be in probe->mem, with out->ncols columns of the output schema and
+ * room for `out_capacity` rows; a column whose `nulls` is NULL must not receive a NULL (else GSQL_E_INVALID).
+ * On GSQL_E_CAPACITY *out_rows is the required capacity.  Row order is unspecified (the reference's is too:
+ * BaseExecTest.java:78-103 compares multisets). */
+gsql_status gsql_join_probe(gsql_join *j, const gsql_batch *probe, gsql_batch *out, int64_t out_capacity,
+                            int64_t *out_rows);
+/* build_outer only, after the last probe: the unmatched build rows, NULL-padded (nextJoinNullRows). */
+gsql_status gsql_join_unmatched_build(gsql_join *j, gsql_batch *out, int64_t out_capacity, int64_t *out_rows);
+void gsql_join_destroy(gsql_join *j);
+
+/* ------------------------------------------------------------------------------------------------ hash agg */
+typedef struct gsql_agg_call {
+    int32_t kind; /* gsql_agg_kind */
+    int32_t ncols;
+    int32_t cols[4];
+    int32_t filter_arg; /* -1 = none (AggregateCall.filterArg) */
+} gsql_agg_call;
+
+typedef struct gsql_agg_spec {
+    int32_t n_input_cols;
+    int32_t input_types[GSQL_MAX_COLS];
+    int32_t ngroups;
+    int32_t groups[GSQL_MAX_KEYS];
+    int32_t naggs;
+    gsql_agg_call aggs[GSQL_MAX_AGGS];
+    int64_t expected_groups; /* planner estimate; only sizes the first table */
+} gsql_agg_spec;
+
+gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec, gsql_agg **out);
+gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch);          /* consumeChunk */
+gsql_status gsql_agg_finish(gsql_agg *a, int64_t *ngroups);                  /* buildConsume */
+gsql_status gsql_agg_output_schema(gsql_agg *a, int32_t *ncols, int32_t *types /* GSQL_MAX_COLS */);
+/* nextChunk: copies up to max_rows result rows (group keys || aggregate values) starting at the internal cursor
+ * into `out` (out->mem says where); *out_rows == 0 means exhausted.  Every out column needs a nulls buffer. */
+gsql_status gsql_agg_next(gsql_agg *a, gsql_batch *out, int64_t max_rows, int64_t *out_rows);
+void gsql_agg_destroy(gsql_agg *a);
+
+/* ------------------------------------------------------------------------------------------------ exchange */
+typedef struct gsql_xchg_spec {
+    int32_t n_cols;
+    int32_t types[GSQL_MAX_COLS];
+    int32_t n_channels;                 /* partition channels (hash keys) */
+    int32_t channels[GSQL_MAX_KEYS];
+    int32_t key_types[GSQL_MAX_KEYS];   /* keyTargetTypes; same as column type when no conversion */
+    int32_t nparts;                     /* consumers (local exchange) or ranks (remote shuffle) */
+} gsql_xchg_spec;
+
+gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spec, gsql_xchg **out);
+/* Local hash-partition exchange: rows of `in` are grouped by destination into `out` (same schema, capacity >=
+ * in->rows, same mem); part_counts[p] (host memory, nparts entries) = rows routed to p; destination p's rows are
+ * out rows [sum(part_counts[0..p)), +part_counts[p]).  Order inside a destination is unspecified. */
+gsql_status gsql_xchg_partition(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t *part_counts);
+
+/* Multi-GPU shuffle (one process per GPU).  Rank 0 creates the id, the caller broadcasts the 128 bytes by any
+ * means (torch.distributed, the MPP coordinator), every rank calls comm_init. */
+gsql_status gsql_comm_unique_id(uint8_t id[128]);
+gsql_status gsql_comm_init(gsql_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t id[128]);
+gsql_status gsql_comm_destroy(gsql_ctx *ctx);
+/* Partition `in` (device) by destination rank, exchange counts, and AllToAllv the column segments over
+ * NVLink/NVSwitch.  `out` (device) must hold out_capacity rows; on GSQL_E_CAPACITY *out_rows is the need.
+ * recv_counts (host, nranks entries, may be NULL) = rows received from each source rank. */
+gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t out_capacity,
+                                 int64_t *out_rows, int64_t *recv_counts);
+void gsql_xchg_destroy(gsql_xchg *x);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSQL_GPU_H */

@@ -1,0 +1,263 @@
+"""GPU parity tests proper: libgsql_gpu.so (through the C-ABI) against the CPU oracle on identical inputs.
+
+Bars (north_star): integer / COUNT / key / payload columns bit-exact, floating SUM/AVG within 1e-6 relative;
+results compared as order-insensitive row multisets like the reference's own tests (BaseExecTest.java:78-103).
+Run on the B200 box with `pytest -m gpu`.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests import kat_util as ku
+from tests.golden import reference_kats as kats
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6  # north_star tolerance for floating SUM / AVG
+
+
+@pytest.fixture(scope="module")
+def gu():
+    from tests import gpu_util
+    gpu_util.ctx()  # raises loudly if the extension or the device is missing — no CPU fallback
+    return gpu_util
+
+
+# ------------------------------------------------------------------------------------------------ contractual hashes
+def test_hash_rows_and_partition_ids_bit_exact(gu):
+    n = 100_003
+    a = ku.with_nulls((ku.rand_u64(n, 1) % np.uint64(1 << 40)).astype(np.int64) - (1 << 39), 0.03, 2)
+    b = ku.with_nulls((ku.rand_u64(n, 3) % np.uint64(1 << 31)).astype(np.int32), 0.03, 4)
+    d = (ku.rand_u64(n, 5) % np.uint64(1000)).astype(np.float64) / 7.0
+    d[:4] = [0.0, -0.0, np.nan, np.inf]
+    c = ku.with_nulls(d, 0.03, 6)
+    cols = [a, b, c]
+    for keys, ut in [([0], None), ([1], None), ([2], None), ([0, 1, 2], None), ([1, 0], [orc.T_INT64, orc.T_INT64]),
+                     ([1], [orc.T_FP64])]:
+        exp = orc.hash_rows([cols[k] for k in keys], ut)
+        got_h = gu.ctx().hash_rows(cols, keys, ut)
+        got_d = gu.ctx().hash_rows(gu.to_device(cols), keys, ut).cpu().numpy()
+        assert np.array_equal(exp, got_h) and np.array_equal(exp, got_d)
+        for p in (2, 3, 8, 13, 64, 1000):
+            assert np.array_equal(orc.partition_ids(exp, p), gu.ctx().partition_ids(got_h, p))
+
+
+# ------------------------------------------------------------------------------------------------ join KATs
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("case", kats.JOIN_KATS, ids=[c["name"] for c in kats.JOIN_KATS])
+def test_join_kat(gu, case, mem):
+    from galaxysql_b200 import native as N
+    spec, outer, inner, expect, err = ku.join_case(case)
+    if err:
+        with pytest.raises(N.MoreThanOneRowError):
+            gu.gpu_hash_join(spec, outer, inner, mem=mem)
+        return
+    got = gu.gpu_hash_join(spec, outer, inner, mem=mem, build_batches=2 if len(inner[0][0]) else 1)
+    assert ku.rows_multiset(got) == expect
+
+
+def _rand_tables(n_in, n_out, key_mod_in, key_mod_out, null_frac, seed, key_dtype=np.int64):
+    ik = (ku.rand_u64(n_in, seed) % np.uint64(key_mod_in)).astype(key_dtype)
+    ok = (ku.rand_u64(n_out, seed + 1) % np.uint64(key_mod_out)).astype(key_dtype)
+    inner = [ku.with_nulls(ik, null_frac, seed + 2), ku.with_nulls((ku.rand_u64(n_in, seed + 3) % np.uint64(1000)).astype(np.int32), null_frac, seed + 4),
+             ((ku.rand_u64(n_in, seed + 5) % np.uint64(1 << 20)).astype(np.float64), None)]
+    outer = [ku.with_nulls(ok, null_frac, seed + 6), ku.with_nulls((ku.rand_u64(n_out, seed + 7) % np.uint64(1000)).astype(np.int32), null_frac, seed + 8),
+             ((ku.rand_u64(n_out, seed + 9) % np.uint64(1 << 20)).astype(np.int64), None)]
+    return outer, inner
+
+
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_RIGHT, orc.JOIN_SEMI, orc.JOIN_ANTI])
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_join_random_vs_oracle(gu, jt, mem):
+    outer, inner = _rand_tables(20_000, 50_000, 6_000, 8_000, 0.02, seed=100 + jt)   # duplicates on both sides
+    spec = orc.JoinSpec(jt, [0], [0], [orc.T_INT64])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    got = ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem=mem, build_batches=3, probe_batches=2))
+    assert got == exp
+
+
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_RIGHT])
+def test_join_build_outer_vs_oracle(gu, jt):
+    outer, inner = _rand_tables(7_000, 9_000, 3_000, 3_500, 0.03, seed=300 + jt)
+    spec = orc.JoinSpec(jt, [0], [0], [orc.T_INT64], build_outer=True)
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="device", probe_batches=3)) == exp
+
+
+def test_join_multi_key_mixed_types(gu):
+    outer, inner = _rand_tables(5_000, 12_000, 40, 50, 0.05, seed=400)
+    # keys: (int64 col0, int32 col1) ; second key unified INT32 vs INT32 ; plus a widening INT32->INT64 case
+    spec = orc.JoinSpec(orc.JOIN_INNER, [0, 1], [0, 1], [orc.T_INT64, orc.T_INT32])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner)) == exp
+    spec = orc.JoinSpec(orc.JOIN_LEFT, [1], [0], [orc.T_INT64])   # outer int32 col vs inner int64 col, unified BIGINT
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="device")) == exp
+
+
+def test_join_double_key(gu):
+    n_in, n_out = 3000, 4000
+    ik = (ku.rand_u64(n_in, 1) % np.uint64(500)).astype(np.float64) * 0.5
+    ok = (ku.rand_u64(n_out, 2) % np.uint64(700)).astype(np.float64) * 0.5
+    inner = [(ik, None), (np.arange(n_in, dtype=np.int32), None)]
+    outer = [(ok, None), (np.arange(n_out, dtype=np.int32), None)]
+    spec = orc.JoinSpec(orc.JOIN_INNER, [0], [0], [orc.T_FP64])
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner)) == ku.rows_multiset(orc.hash_join(spec, outer, inner))
+
+
+def test_join_edge_cases(gu):
+    e64 = np.zeros(0, np.int64)
+    e32 = np.zeros(0, np.int32)
+    k = np.array([1, 2, 3, -2**63, 2**63 - 1, -1, 0], dtype=np.int64)       # includes the table's empty marker
+    inner = [(k, None), (np.arange(7, dtype=np.int32), None)]
+    outer = [(np.array([-2**63, 0, 5, -1, 2**63 - 1, -2**63], dtype=np.int64), None), (np.arange(6, dtype=np.int32), None)]
+    for jt in (orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_SEMI, orc.JOIN_ANTI):
+        spec = orc.JoinSpec(jt, [0], [0], [orc.T_INT64])
+        assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner)) == ku.rows_multiset(orc.hash_join(spec, outer, inner))
+        # empty probe / empty build
+        assert ku.rows_multiset(gu.gpu_hash_join(spec, [(e64, None), (e32, None)], inner)) == \
+            ku.rows_multiset(orc.hash_join(spec, [(e64, None), (e32, None)], inner))
+        assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, [(e64, None), (e32, None)])) == \
+            ku.rows_multiset(orc.hash_join(spec, outer, [(e64, None), (e32, None)]))
+
+
+def test_join_heavy_duplicates(gu):
+    """One hot build key with thousands of duplicates (chain walk + exact two-pass sizing)."""
+    n_in, n_out = 6000, 300
+    ik = np.where(np.arange(n_in) % 2 == 0, 7, np.arange(n_in)).astype(np.int64)
+    ok = (np.arange(n_out) % 10).astype(np.int64)
+    inner = [(ik, None), (np.arange(n_in, dtype=np.int32), None)]
+    outer = [(ok, None), (np.arange(n_out, dtype=np.int32), None)]
+    spec = orc.JoinSpec(orc.JOIN_INNER, [0], [0], [orc.T_INT64])
+    exp = orc.hash_join(spec, outer, inner)
+    got = gu.gpu_hash_join(spec, outer, inner, mem="device")
+    assert len(got[0][0]) == len(exp[0][0]) == 30 * 3000 + 30 * 1
+    assert ku.rows_multiset(got) == ku.rows_multiset(exp)
+
+
+def test_join_c2_shape_scaled(gu):
+    """BASELINE config 2 at 1/100 scale: unique BIGINT build key (permutation) + 2 INT payloads, every probe row
+    matches exactly once.  Bit-exact against the oracle, plus the size-independent properties used at full size."""
+    nb, npr = 1_000_000, 10_000_000
+    perm = np.argsort(ku.rand_u64(nb, 42)).astype(np.int64)
+    inner = [(perm, None), ((ku.rand_u64(nb, 43) >> np.uint64(33)).astype(np.int32), None), ((ku.rand_u64(nb, 44) >> np.uint64(33)).astype(np.int32), None)]
+    outer = [((ku.rand_u64(npr, 45) % np.uint64(nb)).astype(np.int64), None), ((ku.rand_u64(npr, 46) >> np.uint64(33)).astype(np.int32), None),
+             ((ku.rand_u64(npr, 47) >> np.uint64(33)).astype(np.int32), None)]
+    spec = orc.JoinSpec(orc.JOIN_INNER, [0], [0], [orc.T_INT64])
+    got = gu.gpu_hash_join(spec, outer, inner, mem="device")
+    assert len(got[0][0]) == npr
+    assert np.array_equal(got[0][0], got[3][0])                      # probe.key == build.key on every row
+    # payload of the build row with that key (direct lookup through the permutation's inverse)
+    inv = np.empty(nb, np.int64); inv[perm] = np.arange(nb)
+    assert np.array_equal(got[4][0], inner[1][0][inv[got[0][0]]]) and np.array_equal(got[5][0], inner[2][0][inv[got[0][0]]])
+    # probe side is a permutation of the input probe rows: checksum of (key, p1, p2) triples
+    def cks(k, a, b):
+        return int(np.bitwise_xor.reduce(ku.splitmix64(k.astype(np.uint64) * np.uint64(3) + a.astype(np.uint64) * np.uint64(5) + b.astype(np.uint64))))
+    assert cks(got[0][0], got[1][0], got[2][0]) == cks(outer[0][0], outer[1][0], outer[2][0])
+    # and bit-exact against the oracle on a 1M-row slice
+    sl = slice(0, 1_000_000)
+    o2 = [(d[sl], None) for d, _ in outer]
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, o2, inner, mem="device")) == ku.rows_multiset(orc.hash_join(spec, o2, inner))
+
+
+# ------------------------------------------------------------------------------------------------ aggregation
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("case", kats.AGG_KATS, ids=[c["name"] for c in kats.AGG_KATS])
+def test_agg_kat(gu, case, mem):
+    cols, groups, aggs, expected_groups, expect = ku.agg_case(case)
+    got = gu.gpu_hash_agg(cols, groups, aggs, expected_groups, mem=mem, batches=2)
+    assert ku.rows_multiset(got) == expect
+
+
+@pytest.mark.parametrize("aggset", kats.AGG_SEQUENCE_INPUT["agg_sets"])
+def test_agg_sequence_chunks(gu, aggset):
+    inp = kats.AGG_SEQUENCE_INPUT
+    cols = ku.chunks_to_cols(inp["chunks"], inp["types"], {})
+    aggs = ku.agg_calls(aggset)
+    assert ku.rows_multiset(gu.gpu_hash_agg(cols, inp["groups"], aggs, 100, batches=3)) == \
+        ku.rows_multiset(orc.hash_agg(cols, inp["groups"], aggs, 100))
+
+
+def test_agg_c1_count_star(gu):
+    """BASELINE config 1: SELECT k, COUNT(*) FROM t GROUP BY k — 1M-row INT column, k in [0, 65536)."""
+    n = 1_000_000
+    k = (ku.rand_u64(n, 42) % np.uint64(65536)).astype(np.int32)
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR)]
+    exp = orc.hash_agg([(k, None)], [0], aggs, 65535)
+    for mem in ("host", "device"):
+        got = gu.gpu_hash_agg([(k, None)], [0], aggs, 65535, mem=mem)
+        assert ku.rows_multiset(got) == ku.rows_multiset(exp)
+
+
+def test_agg_all_kinds_with_nulls(gu):
+    n = 300_000
+    k1 = ku.with_nulls((ku.rand_u64(n, 1) % np.uint64(3000)).astype(np.int64), 0.01, 2)
+    k2 = ku.with_nulls((ku.rand_u64(n, 3) % np.uint64(5)).astype(np.int32), 0.01, 4)
+    vd = ku.with_nulls((ku.rand_u64(n, 5) % np.uint64(100000)).astype(np.float64) / 100.0 - 300.0, 0.01, 6)
+    vi = ku.with_nulls((ku.rand_u64(n, 7) % np.uint64(1 << 20)).astype(np.int32) - (1 << 19), 0.01, 8)
+    vl = ku.with_nulls((ku.rand_u64(n, 9) >> np.uint64(2)).astype(np.int64), 0.01, 10)     # ~2^62: SUM overflows long
+    cols = [k1, k2, vd, vi, vl]
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_COUNT, [2]), orc.AggCall(orc.AGG_COUNT, [2, 3]),
+            orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_SUM, [3]),
+            orc.AggCall(orc.AGG_SUM, [4]), orc.AggCall(orc.AGG_MIN, [2]), orc.AggCall(orc.AGG_MAX, [2]),
+            orc.AggCall(orc.AGG_MIN, [3]), orc.AggCall(orc.AGG_MAX, [4]), orc.AggCall(orc.AGG_SUM0, [4])]
+    for groups in ([0], [1], [0, 1], []):
+        exp = orc.hash_agg(cols, groups, aggs, 1024)
+        got = gu.gpu_hash_agg(cols, groups, aggs, 1024, mem="device", batches=4)
+        ng = len(groups)
+        gu.approx_rows_equal(got, exp, float_cols=[ng + 3, ng + 4], key_cols=list(range(ng)), rtol=RTOL)
+
+
+def test_agg_table_growth_high_cardinality(gu):
+    """expected_groups far below reality: the table must grow and re-run the overflowed rows."""
+    n = 1_500_000
+    k = (ku.rand_u64(n, 11) % np.uint64(1_200_000)).astype(np.int64)
+    v = (ku.rand_u64(n, 12) % np.uint64(1000)).astype(np.float64)
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1])]
+    exp = orc.hash_agg([(k, None), (v, None)], [0], aggs, 1024)
+    got = gu.gpu_hash_agg([(k, None), (v, None)], [0], aggs, 1024, mem="device", batches=2)
+    gu.approx_rows_equal(got, exp, float_cols=[2], key_cols=[0], rtol=RTOL)
+
+
+def test_agg_edge_cases(gu):
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [0])]
+    empty = [(np.zeros(0, np.int64), None)]
+    for groups in ([0], []):
+        assert ku.rows_multiset(gu.gpu_hash_agg(empty, groups, aggs, 16)) == ku.rows_multiset(orc.hash_agg(empty, groups, aggs, 16))
+    k = np.array([-2**63, -2**63, 2**63 - 1, 0, 0, 0], dtype=np.int64)      # includes the table's empty marker
+    assert ku.rows_multiset(gu.gpu_hash_agg([(k, None)], [0], aggs, 16)) == ku.rows_multiset(orc.hash_agg([(k, None)], [0], aggs, 16))
+
+
+# ------------------------------------------------------------------------------------------------ exchange
+@pytest.mark.parametrize("nparts", [2, 8, 3, 64])
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_partition_exchange_vs_oracle(gu, nparts, mem):
+    n = 200_000
+    k = ku.with_nulls((ku.rand_u64(n, 7) % np.uint64(5000)).astype(np.int64), 0.01, 8)
+    v = (np.arange(n, dtype=np.int32), None)
+    d = ((ku.rand_u64(n, 9) % np.uint64(1000)).astype(np.float64), None)
+    cols = [k, v, d]
+    exp_cols, exp_counts = orc.partition_exchange(cols, [0], nparts)
+    got_cols, got_counts = gu.gpu_partition(cols, [0], nparts, mem=mem)
+    assert np.array_equal(exp_counts, got_counts)
+    off = 0
+    for p in range(nparts):   # same rows per destination (order inside a destination is unspecified)
+        a = [(c[0][off:off + exp_counts[p]], None if c[1] is None else c[1][off:off + exp_counts[p]]) for c in exp_cols]
+        b = [(c[0][off:off + exp_counts[p]], None if c[1] is None else c[1][off:off + exp_counts[p]]) for c in got_cols]
+        assert ku.rows_multiset(a) == ku.rows_multiset(b)
+        off += exp_counts[p]
+
+
+def test_all_to_all_single_rank(gu):
+    """The NCCL path with a 1-rank communicator: partition + self send/recv must return every row."""
+    import torch
+    from galaxysql_b200 import api
+    c = gu.ctx()
+    api.comm_init(c, 1, 0, api.comm_unique_id())
+    n = 50_000
+    cols = [((ku.rand_u64(n, 1) % np.uint64(999)).astype(np.int64), None), (np.arange(n, dtype=np.int32), None)]
+    x = api.Exchange(c, [1, 0], [0], 1)
+    out, recv = x.all_to_all(gu.to_device(cols), capacity=n)
+    assert recv.tolist() == [n]
+    assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
+    c.lib.gsql_comm_destroy(c.ptr)
