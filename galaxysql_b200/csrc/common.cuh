@@ -234,25 +234,31 @@ __host__ __device__ __forceinline__ uint64_t gsql_fmix64(uint64_t x) {
 }
 
 // ------------------------------------------------------------------------------------------------ memory ops
-// Streaming (read-once) loads / write-once stores: keep them out of L1 and first in line for L2 eviction so
-// that hash-table sectors stay resident.
-__device__ __forceinline__ int4 ld_stream_16(const void *p) {
+// Streaming (read-once) loads / write-once stores use the .cs (evict-first) policy so that hash-table sectors stay
+// resident in the 126 MB L2; table reads carry an explicit L2 evict_last cache policy.
+__device__ __forceinline__ int4 ld_stream_16(const void *p) { return __ldcs(reinterpret_cast<const int4 *>(p)); }
+__device__ __forceinline__ long long ld_stream_8(const void *p) { return __ldcs(reinterpret_cast<const long long *>(p)); }
+__device__ __forceinline__ int ld_stream_4(const void *p) { return __ldcs(reinterpret_cast<const int *>(p)); }
+__device__ __forceinline__ void st_stream_16(void *p, const int4 &v) { __stcs(reinterpret_cast<int4 *>(p), v); }
+__device__ __forceinline__ void st_stream_8(void *p, long long v) { __stcs(reinterpret_cast<long long *>(p), v); }
+__device__ __forceinline__ void st_stream_4(void *p, int v) { __stcs(reinterpret_cast<int *>(p), v); }
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ int4 ld_keep_16(const void *p, uint64_t pol) {
     int4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.s32 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ void st_stream_16(void *p, const int4 &v) {
-    asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
-                 "r"(v.z), "r"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void st_stream_8(void *p, long long v) {
-    asm volatile("st.global.L1::no_allocate.L2::evict_first.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_stream_4(void *p, int v) {
-    asm volatile("st.global.L1::no_allocate.L2::evict_first.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long ld_keep_8(const void *p, uint64_t pol) {
+    unsigned long long v;
+    asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
 }
 
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -17,6 +17,8 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "join_fast.cuh"
 
@@ -316,6 +318,7 @@ struct gsql_join {
     DevBuf slots, links, used, flags;
     uint64_t nslots = 0;
     bool any_multi = false;
+    bool generic_built = false;
     bool pass_nothing = false, pass_through = false;
     bool semi_join = false, outer_join = false, single_join = false;
     // output schema
@@ -482,28 +485,153 @@ static void fill_build_cols(gsql_join *j, DColSet *build, KeySet *bkeys) {
     }
 }
 
-extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
-    if (!j) return GSQL_E_INVALID;
-    gsql_ctx *ctx = j->ctx;
-    if (ctx->sticky) return GSQL_E_CUDA;
-    if (j->built) return GSQL_OK;
-    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
-    const gsql_join_spec &s = j->spec;
-    // pass-through / pass-nothing (ParallelHashJoinExec.buildConsume:107-128; doSpecialCheckForSemiJoin:290-310)
-    if (j->build_rows == 0 && s.join_type == GSQL_JOIN_INNER) j->pass_nothing = true;
-    if (j->semi_join) {
-        if (j->build_rows == 0) {
-            if (s.join_type == GSQL_JOIN_SEMI) j->pass_nothing = true;
-            else j->pass_through = true;
-        } else if (s.join_type == GSQL_JOIN_ANTI && s.n_anti_operands > 0 && j->n_build == 1 && j->bhas_nulls[0]) {
-            // x NOT IN (... NULL ...) is never true: need to know whether the single build column holds a NULL
-            std::vector<uint8_t> h((size_t)j->build_rows);
-            GSQL_CUDA(ctx, cudaMemcpyAsync(h.data(), j->bnulls[0].p, (size_t)j->build_rows, cudaMemcpyDeviceToHost, ctx->stream));
-            GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (uint8_t v : h)
-                if (v) { j->pass_nothing = true; break; }
-        }
+
+// ================================================================================================ fast path (host)
+#define FJ_DISPATCH_W(W, ...)                              \
+    switch (W) {                                           \
+    case 1: { constexpr int WW = 1; __VA_ARGS__; } break;  \
+    case 2: { constexpr int WW = 2; __VA_ARGS__; } break;  \
+    case 3: { constexpr int WW = 3; __VA_ARGS__; } break;  \
+    default: { constexpr int WW = 4; __VA_ARGS__; } break; \
     }
+
+static fj::PartGeom fj_geom(gsql_ctx *ctx, int64_t rows, int P, int W) {
+    fj::PartGeom g;
+    g.rows = rows;
+    g.P = P;
+    size_t smem = fj::scatter_smem_bytes(W, P) + 4096;
+    int per_sm = (int)(200 * 1024 / smem);
+    if (per_sm > 6) per_sm = 6;
+    if (per_sm < 1) per_sm = 1;
+    int64_t nblocks = (int64_t)ctx->sm_count * per_sm;
+    int64_t tiles = div_up(rows, fj::TILE);
+    if (nblocks > tiles) nblocks = tiles;
+    if (nblocks < 1) nblocks = 1;
+    g.chunk = div_up(div_up(rows, nblocks), fj::TILE) * fj::TILE;
+    g.nblocks = (int32_t)div_up(rows, g.chunk);
+    if (g.nblocks < 1) g.nblocks = 1;
+    return g;
+}
+
+// Packs `rows` rows of `cols` into partition order: out[rows * W] words.
+static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::Layout &L, int64_t rows, int P, unsigned long long *out,
+                                int32_t *flags, const char *tag) {
+    const int W = L.nwords;
+    fj::PartGeom g = fj_geom(ctx, rows, P, W);
+    int64_t nh = (int64_t)P * g.nblocks;
+    DevBuf hist, offs, tmp;
+    GSQL_TRY(hist.alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_TRY(offs.alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_CUDA(ctx, cudaMemsetAsync((char *)hist.p + nh * 8, 0, 8, ctx->stream));
+    std::string name = std::string("join_fast_hist_") + tag;
+    {
+        KernelScope ks(ctx, name.c_str());
+        fj::k_fj_hist<<<g.nblocks, fj::THREADS, (size_t)P * 4, ctx->stream>>>(cols.c[L.key_col], g, hist.as<int64_t>(), flags);
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    size_t tb = 0;
+    GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist.as<int64_t>(), offs.as<int64_t>(), nh + 1, ctx->stream));
+    GSQL_TRY(tmp.alloc(ctx, tb));
+    name = std::string("join_fast_scan_") + tag;
+    {
+        KernelScope ks(ctx, name.c_str());
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist.as<int64_t>(), offs.as<int64_t>(), nh + 1, ctx->stream));
+    }
+    size_t smem = fj::scatter_smem_bytes(W, P);
+    name = std::string("join_fast_scatter_") + tag;
+    {
+        KernelScope ks(ctx, name.c_str());
+        FJ_DISPATCH_W(W, {
+            GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            fj::k_fj_scatter<WW><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
+        });
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    return GSQL_OK;
+}
+
+static int64_t env_i64(const char *name, int64_t dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoll(v) : dflt;
+}
+
+// Decides eligibility, builds the packed-row table; leaves j->fast.enabled = false when the generic path must run.
+static gsql_status fast_build(gsql_join *j) {
+    gsql_ctx *ctx = j->ctx;
+    const gsql_join_spec &s = j->spec;
+    JoinFast &F = j->fast;
+    F.enabled = false;
+    if (env_i64("GSQL_JOIN_NO_FAST", 0)) return GSQL_OK;
+    if (s.nkeys != 1 || s.build_outer || j->single_join || s.n_cond > 0) return GSQL_OK;
+    if (s.key_type[0] != GSQL_T_INT32 && s.key_type[0] != GSQL_T_INT64) return GSQL_OK;
+    if (j->build_types[j->bkey_cols[0]] == GSQL_T_FP64 || j->probe_types[j->pkey_cols[0]] == GSQL_T_FP64) return GSQL_OK;
+    if (s.key_type[0] == GSQL_T_INT32 && (j->build_types[j->bkey_cols[0]] != GSQL_T_INT32 || j->probe_types[j->pkey_cols[0]] != GSQL_T_INT32))
+        return GSQL_OK;  // a BIGINT column narrowed to INT would not be the reference's conversion
+    if (j->pass_nothing || j->pass_through || j->build_rows == 0) return GSQL_OK;
+    for (int i = 0; i < j->n_build; i++)
+        if (j->bhas_nulls[i]) return GSQL_OK;
+    if (!fj::make_layout(j->build_types, j->n_build, j->bkey_cols[0], &F.bl)) return GSQL_OK;
+    if (!fj::make_layout(j->probe_types, j->n_probe, j->pkey_cols[0], &F.pl)) return GSQL_OK;
+    F.eligible = true;
+    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 32ll << 20);
+    if (F.part_bytes < 4096) F.part_bytes = 4096;
+    F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 256ll << 20);
+    if (F.sub_batch < fj::TILE) F.sub_batch = fj::TILE;
+    const int BW = F.bl.nwords;
+    int64_t want = j->build_rows * 2;
+    if (want < 1024) want = 1024;
+    int64_t P = div_up(want * BW * 8, F.part_bytes);
+    if (P > fj::MAX_P) P = fj::MAX_P;
+    if (P < 1) P = 1;
+    int64_t spp = div_up(want, P);
+    F.P = (int)P;
+    F.nslots = (uint64_t)(spp * P);
+    GSQL_TRY(F.table.alloc(ctx, (size_t)F.nslots * BW * 8));
+    GSQL_TRY(F.flags.alloc(ctx, fj::FL_COUNT * 4));
+    GSQL_TRY(F.cursor.alloc(ctx, 16));
+    GSQL_CUDA(ctx, cudaMemsetAsync(F.flags.p, 0, fj::FL_COUNT * 4, ctx->stream));
+    {
+        KernelScope ks(ctx, "join_fast_table_init");
+        int grid = grid_rows(ctx, (int64_t)F.nslots, 256, 8);
+        FJ_DISPATCH_W(BW, { fj::k_fj_table_init<WW><<<grid, 256, 0, ctx->stream>>>(F.table.as<unsigned long long>(), F.nslots); });
+    }
+    DColSet build;
+    KeySet bkeys;
+    fill_build_cols(j, &build, &bkeys);
+    DevBuf packed;
+    const unsigned long long *src = nullptr;
+    if (F.P > 1) {
+        GSQL_TRY(packed.alloc(ctx, (size_t)j->build_rows * BW * 8));
+        GSQL_TRY(fj_partition(ctx, build, F.bl, j->build_rows, F.P, packed.as<unsigned long long>(), F.flags.as<int32_t>(), "build"));
+        src = packed.as<unsigned long long>();
+    }
+    {
+        KernelScope ks(ctx, "join_fast_insert");
+        int grid = grid_rows(ctx, div_up(j->build_rows, fj::RPT), 256, 6);
+        FJ_DISPATCH_W(BW, {
+            fj::k_fj_insert<WW><<<grid, fj::THREADS, 0, ctx->stream>>>(src, build, F.bl, j->build_rows, F.table.as<unsigned long long>(), F.nslots,
+                                                                       F.flags.as<int32_t>());
+        });
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    int32_t hf[fj::FL_COUNT];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hf, F.flags.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hf[fj::FL_SENTINEL] || hf[fj::FL_DUP] || hf[fj::FL_DISP]) {  // not a unique-key table: generic chained path
+        F.table.release();
+        return GSQL_OK;
+    }
+    GSQL_CUDA(ctx, cudaMemsetAsync(F.flags.p, 0, fj::FL_COUNT * 4, ctx->stream));
+    F.enabled = true;
+    return GSQL_OK;
+}
+
+
+// Builds the generic chained table (lazily: the fast path only needs it for batches it cannot take).
+static gsql_status ensure_generic(gsql_join *j) {
+    if (j->generic_built) return GSQL_OK;
+    gsql_ctx *ctx = j->ctx;
+    const gsql_join_spec &s = j->spec;
     j->nslots = (uint64_t)(j->build_rows * 2 > 64 ? j->build_rows * 2 : 64);
     GSQL_TRY(j->slots.alloc(ctx, (size_t)(j->nslots + 1) * sizeof(Slot)));
     GSQL_TRY(j->links.alloc(ctx, (size_t)(j->build_rows > 0 ? j->build_rows : 1) * 4));
@@ -528,6 +656,34 @@ extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
     GSQL_CUDA(ctx, cudaMemcpyAsync(hflags, j->flags.p, sizeof(hflags), cudaMemcpyDeviceToHost, ctx->stream));
     GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     j->any_multi = hflags[F_ANY_MULTI] != 0;
+    j->generic_built = true;
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
+    if (!j) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (j->built) return GSQL_OK;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const gsql_join_spec &s = j->spec;
+    // pass-through / pass-nothing (ParallelHashJoinExec.buildConsume:107-128; doSpecialCheckForSemiJoin:290-310)
+    if (j->build_rows == 0 && s.join_type == GSQL_JOIN_INNER) j->pass_nothing = true;
+    if (j->semi_join) {
+        if (j->build_rows == 0) {
+            if (s.join_type == GSQL_JOIN_SEMI) j->pass_nothing = true;
+            else j->pass_through = true;
+        } else if (s.join_type == GSQL_JOIN_ANTI && s.n_anti_operands > 0 && j->n_build == 1 && j->bhas_nulls[0]) {
+            // x NOT IN (... NULL ...) is never true: need to know whether the single build column holds a NULL
+            std::vector<uint8_t> h((size_t)j->build_rows);
+            GSQL_CUDA(ctx, cudaMemcpyAsync(h.data(), j->bnulls[0].p, (size_t)j->build_rows, cudaMemcpyDeviceToHost, ctx->stream));
+            GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (uint8_t v : h)
+                if (v) { j->pass_nothing = true; break; }
+        }
+    }
+    GSQL_TRY(fast_build(j));
+    if (!j->fast.enabled) GSQL_TRY(ensure_generic(j));
     j->built = true;
     return GSQL_OK;
 }
@@ -544,8 +700,9 @@ extern "C" gsql_status gsql_join_info_get(gsql_join *j, gsql_join_info *info) {
     info->has_duplicate_keys = j->any_multi;
     info->pass_through = j->pass_through;
     info->pass_nothing = j->pass_nothing;
-    info->fast_path = 0;
-    info->partitions = 1;
+    info->fast_path = j->fast.enabled ? 1 : 0;
+    info->partitions = j->fast.enabled ? j->fast.P : 1;
+    if (j->fast.enabled) { info->table_slots = (int64_t)j->fast.nslots; info->table_bytes = (int64_t)j->fast.table.bytes; info->device_bytes += (int64_t)j->fast.table.bytes; }
     return GSQL_OK;
 }
 
@@ -688,6 +845,88 @@ gsql_status download_outputs(gsql_join *j, gsql_batch *out, int64_t rows, const 
     return GSQL_OK;
 }
 
+// Probe through the packed single-key table.  *handled = false leaves the batch to the generic path.
+static gsql_status fast_probe(gsql_join *j, const StagedBatch &sp, const gsql_batch *probe, gsql_batch *out, int64_t out_capacity,
+                              int64_t *out_rows, bool *handled) {
+    *handled = false;
+    JoinFast &F = j->fast;
+    gsql_ctx *ctx = j->ctx;
+    if (!F.enabled) return GSQL_OK;
+    const int64_t n = sp.rows;
+    if (out_capacity < n) return GSQL_OK;  // <= 1 output row per probe row; smaller buffers take the exact two-pass path
+    for (int i = 0; i < sp.ncols; i++)
+        if (probe->cols[i].nulls) return GSQL_OK;
+    const int jt = j->spec.join_type;
+    if (j->outer_join)
+        for (int q = 0; q < j->nout; q++)
+            if (j->out_side[q] == SIDE_BUILD && !out->cols[q].nulls)
+                return gsql_set_error(ctx, GSQL_E_INVALID, "outer join: output column %d needs a nulls buffer", q);
+    ProbeWork w;
+    ProbeParams PP;
+    GSQL_TRY(fill_params(j, sp, &PP));
+    GSQL_TRY(bind_outputs(j, out, n, &PP, &w));
+    fj::OutMap O;
+    memset(&O, 0, sizeof(O));
+    O.nout = j->nout;
+    O.join_type = jt;
+    for (int q = 0; q < j->nout; q++) {
+        const fj::Layout &L = j->out_side[q] == SIDE_PROBE ? F.pl : F.bl;
+        O.data[q] = PP.out[q].data;
+        O.nulls[q] = PP.out[q].nulls;
+        O.side[q] = (int8_t)(j->out_side[q] == SIDE_PROBE ? 0 : 1);
+        O.word[q] = (int8_t)L.word[j->out_col[q]];
+        O.half[q] = (int8_t)L.half[j->out_col[q]];
+        O.is32[q] = (int8_t)(j->out_types[q] == GSQL_T_INT32);
+    }
+    GSQL_CUDA(ctx, cudaMemsetAsync(F.cursor.p, 0, 16, ctx->stream));
+    const int PW = F.pl.nwords, BW = F.bl.nwords;
+    DColSet cols;
+    memset(&cols, 0, sizeof(cols));
+    cols.n = sp.ncols;
+    DevBuf packed;
+    const int64_t sub = F.P > 1 ? (F.sub_batch < n ? F.sub_batch : n) : n;
+    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)sub * PW * 8));
+    for (int64_t lo = 0; lo < n; lo += sub) {
+        int64_t m = n - lo < sub ? n - lo : sub;
+        for (int i = 0; i < sp.ncols; i++) {
+            cols.c[i] = sp.cols[i];
+            cols.c[i].data = (const char *)sp.cols[i].data + (size_t)lo * gsql_type_width(sp.cols[i].type);
+        }
+        const unsigned long long *src = nullptr;
+        if (F.P > 1) {
+            GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed.as<unsigned long long>(), F.flags.as<int32_t>(), "probe"));
+            src = packed.as<unsigned long long>();
+        }
+        {
+            KernelScope ks(ctx, "join_fast_probe");
+            int grid = (int)div_up(m, fj::TILE);
+#define FJ_PROBE_CASE(PWv, BWv)                                                                                                         \
+    if (PW == PWv && BW == BWv)                                                                                                         \
+        fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, 0, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
+                                                                       F.cursor.as<unsigned long long>(), F.flags.as<int32_t>());
+            FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
+            FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
+            FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
+            FJ_PROBE_CASE(4, 1) FJ_PROBE_CASE(4, 2) FJ_PROBE_CASE(4, 3) FJ_PROBE_CASE(4, 4)
+#undef FJ_PROBE_CASE
+        }
+        GSQL_CUDA(ctx, cudaGetLastError());
+    }
+    unsigned long long total = 0;
+    int32_t hf[fj::FL_COUNT];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(&total, F.cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hf, F.flags.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hf[fj::FL_NULLOUT]) {
+        cudaMemsetAsync(F.flags.p, 0, fj::FL_COUNT * 4, ctx->stream);
+        return gsql_set_error(ctx, GSQL_E_INVALID, "a NULL had to be written into an output column without a nulls buffer");
+    }
+    GSQL_TRY(download_outputs(j, out, (int64_t)total, PP));
+    *out_rows = out->rows = (int64_t)total;
+    *handled = true;
+    return GSQL_OK;
+}
+
 }  // namespace
 
 extern "C" gsql_status gsql_join_probe_count(gsql_join *j, const gsql_batch *probe, int64_t *out_rows) {
@@ -701,6 +940,7 @@ extern "C" gsql_status gsql_join_probe_count(gsql_join *j, const gsql_batch *pro
     if (j->pass_nothing) return GSQL_OK;
     if (j->pass_through) { *out_rows = probe->rows; return GSQL_OK; }
     if (probe->rows == 0) return GSQL_OK;
+    GSQL_TRY(ensure_generic(j));
     ProbeWork w;
     GSQL_TRY(stage_batch(ctx, probe, &w.probe));
     ProbeParams P;
@@ -741,6 +981,12 @@ extern "C" gsql_status gsql_join_probe(gsql_join *j, const gsql_batch *probe, gs
     }
     ProbeWork w;
     GSQL_TRY(stage_batch(ctx, probe, &w.probe));
+    if (j->fast.enabled) {
+        bool handled = false;
+        GSQL_TRY(fast_probe(j, w.probe, probe, out, out_capacity, out_rows, &handled));
+        if (handled) return GSQL_OK;
+    }
+    GSQL_TRY(ensure_generic(j));
     ProbeParams P;
     GSQL_TRY(fill_params(j, w.probe, &P));
     int64_t total = 0;
@@ -774,6 +1020,7 @@ extern "C" gsql_status gsql_join_unmatched_build(gsql_join *j, gsql_batch *out, 
     out->rows = 0;
     if (!j->spec.build_outer || !j->outer_join || j->build_rows == 0) return GSQL_OK;
     GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    GSQL_TRY(ensure_generic(j));
     ProbeWork w;
     w.probe.rows = 0;
     w.probe.ncols = j->n_probe;

@@ -1,7 +1,429 @@
-// join_fast.cuh — single-integer-key specialisation of the join (filled in by join_fast.cu).
+// join_fast.cuh — radix-partitioned, L2-resident hash join for a single integer equi-key (the C2 / TPC-H shape).
+//
+// Why: on B200 a random 16-byte table read costs ~35 G reads/s when the table lives in HBM but ~230 G reads/s when
+// the touched slice of the table fits the 126 MB L2 (tools/microbench.cu, profiles/r01_microbench.txt).  So both
+// sides are range-partitioned on the TABLE SLOT (partition = slot / slots_per_partition = mulhi(fmix64(key), P)),
+// rows are packed into fixed-stride 8-byte-word rows {key, payload...}, and the probe walks partition after
+// partition so that the active slice of the table (<= ~32 MB) stays L2-resident while probe rows stream through
+// with evict-first loads/stores.  Every pass is a pure streaming pass over HBM:
+//     k_fj_hist     keys only          ->  [partition][block] histogram
+//     k_fj_scatter  all columns        ->  packed rows in partition order (shared-memory staged, full-sector writes)
+//     k_fj_insert   packed build rows  ->  open-addressing table of packed rows (key CAS, payload inline)
+//     k_fj_probe    packed probe rows  ->  output columns (one table read per probe row, warp-ballot compaction,
+//                                          one global cursor bump per 2048-row tile)
+// The table holds whole build rows inline (stride = key + payload words), so a probe is ONE L2 access; duplicate
+// build keys, NULLs, composite/double keys, non-equi conditions and outer-build joins take the generic path in
+// join.cu (same results, two-pass sizing).
+//
+// Reference behaviour preserved: AbstractBufferedJoinExec.nextRows:185-264 for INNER / LEFT / RIGHT / SEMI / ANTI
+// with unique build keys and no NULLs (row multiset identical; output order is unspecified in both).
 #pragma once
+
+#include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
+namespace fj {
+
+constexpr unsigned long long KEY_EMPTY = 0x8000000000000000ULL;
+constexpr int THREADS = 256;
+constexpr int RPT = 8;                 // rows per thread per tile
+constexpr int TILE = THREADS * RPT;    // 2048 rows
+constexpr int MAX_WORDS = 4;           // packed row = key word + up to 3 payload words
+constexpr int MAX_P = 1024;
+constexpr int MAX_DISP = 4096;         // insert gives up (generic path) beyond this displacement
+enum { FL_SENTINEL = 0, FL_DUP = 1, FL_DISP = 2, FL_NULLOUT = 3, FL_COUNT = 4 };
+
+struct Layout {
+    int32_t nwords, ncols, key_col, key_i32;
+    int32_t word[GSQL_MAX_COLS];
+    int32_t half[GSQL_MAX_COLS];  // 0 = low 32 bits, 1 = high 32 bits, 2 = whole word
+};
+
+// Returns false when the side does not fit the packed-row format.
+static bool make_layout(const int32_t *types, int ncols, int key_col, Layout *L) {
+    memset(L, 0, sizeof(*L));
+    L->ncols = ncols;
+    L->key_col = key_col;
+    L->key_i32 = types[key_col] == GSQL_T_INT32;
+    int next = 1;
+    int open_word = -1;  // a word whose high half is still free
+    for (int c = 0; c < ncols; c++) {
+        if (c == key_col) {
+            L->word[c] = 0;
+            L->half[c] = L->key_i32 ? 0 : 2;  // an INT32 key is stored widened; its low half is the column value
+            continue;
+        }
+        if (types[c] == GSQL_T_INT32) {
+            if (open_word >= 0) {
+                L->word[c] = open_word;
+                L->half[c] = 1;
+                open_word = -1;
+            } else {
+                L->word[c] = next;
+                L->half[c] = 0;
+                open_word = next++;
+            }
+        } else {
+            L->word[c] = next++;
+            L->half[c] = 2;
+        }
+    }
+    L->nwords = next;
+    return next <= MAX_WORDS;
+}
+
+__device__ __forceinline__ uint64_t key_hash(unsigned long long k) { return gsql_fmix64(k); }
+
+template <int W>
+__device__ __forceinline__ void pack_row(const DColSet &cols, const Layout &L, int64_t r, unsigned long long (&w)[W]) {
+#pragma unroll
+    for (int i = 0; i < W; i++) w[i] = 0;
+#pragma unroll 1
+    for (int c = 0; c < L.ncols; c++) {
+        const DCol &col = cols.c[c];
+        unsigned long long v;
+        if (col.type == GSQL_T_INT32) {
+            int x = ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
+            v = c == L.key_col ? (unsigned long long)(long long)x : (unsigned long long)(unsigned)x;
+        } else {
+            v = (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+        }
+        int wi = L.word[c];
+        if (L.half[c] == 1) v <<= 32;
+#pragma unroll
+        for (int i = 0; i < W; i++)
+            if (i == wi) w[i] |= v;
+    }
+}
+
+__device__ __forceinline__ unsigned long long load_key(const DCol &col, int64_t r) {
+    if (col.type == GSQL_T_INT32) return (unsigned long long)(long long)ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
+    return (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+}
+
+struct PartGeom {
+    int64_t rows, chunk;  // rows per block (multiple of TILE)
+    int32_t P, nblocks;
+};
+
+// ---- pass 1: histogram of partition ids, keys only
+__global__ void __launch_bounds__(THREADS) k_fj_hist(DCol keycol, PartGeom g, int64_t *__restrict__ hist, int32_t *flags) {
+    extern __shared__ unsigned int sh_hist[];
+    for (int i = threadIdx.x; i < g.P; i += THREADS) sh_hist[i] = 0;
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * g.chunk;
+    int64_t r1 = r0 + g.chunk < g.rows ? r0 + g.chunk : g.rows;
+    bool sentinel = false;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += THREADS) {
+        unsigned long long k = load_key(keycol, r);
+        sentinel |= k == KEY_EMPTY;
+        atomicAdd(&sh_hist[(unsigned)__umul64hi(key_hash(k), (uint64_t)g.P)], 1u);
+    }
+    if (sentinel) flags[FL_SENTINEL] = 1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.P; i += THREADS) hist[(int64_t)i * g.nblocks + blockIdx.x] = sh_hist[i];
+}
+
+// ---- pass 2: pack rows and scatter them into partition order through a shared-memory staged tile
+template <int W>
+__global__ void __launch_bounds__(THREADS) k_fj_scatter(const __grid_constant__ DColSet cols, const __grid_constant__ Layout L, PartGeom g,
+                                                        const int64_t *__restrict__ offs, unsigned long long *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem_raw);           // TILE * W
+    unsigned long long *cur = stage + (size_t)TILE * W;                                      // P
+    unsigned int *hist = reinterpret_cast<unsigned int *>(cur + g.P);                        // P
+    unsigned int *start = hist + g.P;                                                        // P
+    unsigned short *spid = reinterpret_cast<unsigned short *>(start + g.P);                  // TILE
+    typedef cub::BlockScan<unsigned int, THREADS> BlockScan;
+    __shared__ typename BlockScan::TempStorage scan_tmp;
+
+    for (int p = threadIdx.x; p < g.P; p += THREADS) {
+        cur[p] = (unsigned long long)offs[(int64_t)p * g.nblocks + blockIdx.x];
+        hist[p] = 0;
+    }
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * g.chunk;
+    int64_t r1 = r0 + g.chunk < g.rows ? r0 + g.chunk : g.rows;
+    for (int64_t t0 = r0; t0 < r1; t0 += TILE) {
+        unsigned long long w[RPT][W];
+        unsigned int pid[RPT], rank[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            pid[k] = 0xffffffffu;
+            if (r < r1) {
+                pack_row<W>(cols, L, r, w[k]);
+                pid[k] = (unsigned)__umul64hi(key_hash(w[k][0]), (uint64_t)g.P);
+                rank[k] = atomicAdd(&hist[pid[k]], 1u);
+            }
+        }
+        __syncthreads();
+        {  // exclusive scan of hist[0..P) -> start[]
+            constexpr int IPT = MAX_P / THREADS;
+            unsigned int v[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                int p = threadIdx.x * IPT + i;
+                v[i] = p < g.P ? hist[p] : 0;
+            }
+            BlockScan(scan_tmp).ExclusiveSum(v, v);
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                int p = threadIdx.x * IPT + i;
+                if (p < g.P) start[p] = v[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            if (pid[k] != 0xffffffffu) {
+                unsigned int pos = start[pid[k]] + rank[k];
+#pragma unroll
+                for (int i = 0; i < W; i++) stage[(size_t)pos * W + i] = w[k][i];
+                spid[pos] = (unsigned short)pid[k];
+            }
+        }
+        __syncthreads();
+        int n_tile = (int)(r1 - t0 < TILE ? r1 - t0 : TILE);
+        for (int i = threadIdx.x; i < n_tile; i += THREADS) {  // consecutive threads -> consecutive addresses of a run
+            unsigned int p = spid[i];
+            unsigned long long dst = cur[p] + (unsigned)(i - start[p]);
+            if (W == 2) {
+                st_stream_16(out + dst * 2, *reinterpret_cast<const int4 *>(stage + (size_t)i * 2));
+            } else {
+#pragma unroll
+                for (int j = 0; j < W; j++) st_stream_8(out + dst * W + j, (long long)stage[(size_t)i * W + j]);
+            }
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < g.P; p += THREADS) {
+            cur[p] += hist[p];
+            hist[p] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+static size_t scatter_smem_bytes(int W, int P) { return (size_t)TILE * W * 8 + (size_t)P * 8 + (size_t)P * 4 * 2 + (size_t)TILE * 2; }
+
+// ---- table
+template <int W>
+__global__ void __launch_bounds__(THREADS) k_fj_table_init(unsigned long long *table, uint64_t nslots) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nslots; i += (uint64_t)gridDim.x * blockDim.x) {
+        table[i * W] = KEY_EMPTY;
+#pragma unroll
+        for (int j = 1; j < W; j++) table[i * W + j] = 0;
+    }
+}
+
+// Inserts rows (packed, or packed on the fly from columns when `packed` == nullptr).  Tiles are taken in index order
+// so that concurrently running blocks work on neighbouring partitions (the table slice stays in L2).
+template <int W>
+__global__ void __launch_bounds__(THREADS) k_fj_insert(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
+                                                       const __grid_constant__ Layout L, int64_t n, unsigned long long *table, uint64_t nslots,
+                                                       int32_t *flags) {
+    for (int64_t t0 = (int64_t)blockIdx.x * TILE; t0 < n; t0 += (int64_t)gridDim.x * TILE) {
+#pragma unroll 1
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            if (r >= n) break;
+            unsigned long long w[W];
+            if (packed) {
+#pragma unroll
+                for (int i = 0; i < W; i++) w[i] = (unsigned long long)ld_stream_8(packed + r * W + i);
+            } else {
+                pack_row<W>(cols, L, r, w);
+            }
+            if (w[0] == KEY_EMPTY) { flags[FL_SENTINEL] = 1; continue; }
+            uint64_t s = __umul64hi(key_hash(w[0]), nslots);
+            int disp = 0;
+            while (true) {
+                unsigned long long *slot = table + s * W;
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot);
+                if (cur == KEY_EMPTY) {
+                    unsigned long long prev = atomicCAS(slot, KEY_EMPTY, w[0]);
+                    if (prev == KEY_EMPTY) {
+#pragma unroll
+                        for (int i = 1; i < W; i++) slot[i] = w[i];
+                        break;
+                    }
+                    cur = prev;
+                }
+                if (cur == w[0]) { flags[FL_DUP] = 1; break; }  // duplicate build key: the generic (chained) path takes over
+                if (++s == nslots) s = 0;
+                if (++disp > MAX_DISP) { flags[FL_DISP] = 1; break; }
+            }
+        }
+    }
+}
+
+// ---- probe
+struct OutMap {
+    void *data[GSQL_MAX_COLS * 2];
+    uint8_t *nulls[GSQL_MAX_COLS * 2];
+    int8_t side[GSQL_MAX_COLS * 2];  // 0 probe, 1 build
+    int8_t word[GSQL_MAX_COLS * 2];
+    int8_t half[GSQL_MAX_COLS * 2];
+    int8_t is32[GSQL_MAX_COLS * 2];
+    int32_t nout;
+    int32_t join_type;
+};
+
+template <int W>
+__device__ __forceinline__ unsigned long long pick(const unsigned long long (&w)[W], int idx) {
+    unsigned long long v = w[0];
+#pragma unroll
+    for (int i = 1; i < W; i++)
+        if (i == idx) v = w[i];
+    return v;
+}
+
+template <int PW, int BW>
+__global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
+                                                      const __grid_constant__ Layout L, int64_t n, const unsigned long long *__restrict__ table,
+                                                      uint64_t nslots, const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
+    __shared__ unsigned int cell[THREADS / 32][RPT];
+    __shared__ unsigned long long tile_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t pol = l2_policy_evict_last();
+    const int64_t t0 = (int64_t)blockIdx.x * TILE;
+    constexpr int BP = BW > 1 ? BW - 1 : 1;
+
+    unsigned long long pw[RPT][PW];
+    unsigned long long bp[RPT][BP];  // build payload words (the build key equals the probe key on a match)
+    unsigned int ballot[RPT];
+    bool found[RPT];
+    uint64_t slot[RPT];
+
+    // 1. stream the probe rows in
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        int64_t r = t0 + k * THREADS + threadIdx.x;
+        if (r < n) {
+            if (packed) {
+                if (PW == 2) {
+                    int4 v = ld_stream_16(packed + r * 2);
+                    pw[k][0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                    pw[k][PW - 1] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PW; i++) pw[k][i] = (unsigned long long)ld_stream_8(packed + r * PW + i);
+                }
+            } else {
+                pack_row<PW>(cols, L, r, pw[k]);
+            }
+            slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PW; i++) pw[k][i] = 0;
+            pw[k][0] = KEY_EMPTY;
+            slot[k] = 0;
+        }
+    }
+    // 2. one L2-resident table read per row (all RPT reads in flight), then the rare collision walks
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        found[k] = false;
+#pragma unroll
+        for (int i = 0; i < BP; i++) bp[k][i] = 0;
+        unsigned long long key = pw[k][0];
+        if (key == KEY_EMPTY) continue;  // padding rows, and the one key value the fast table cannot hold (never built)
+        uint64_t s = slot[k];
+        while (true) {
+            unsigned long long tk;
+            if (BW == 2) {
+                int4 v = ld_keep_16(table + s * 2, pol);
+                tk = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+            } else {
+                tk = ld_keep_8(table + s * BW, pol);
+            }
+            if (tk == key) {
+                if (BW > 2) {
+#pragma unroll
+                    for (int i = 1; i < BW; i++) bp[k][i - 1] = ld_keep_8(table + s * BW + i, pol);
+                }
+                found[k] = true;
+                break;
+            }
+            if (tk == KEY_EMPTY) break;
+            if (++s == nslots) s = 0;
+        }
+    }
+    // 3. which rows emit (AbstractBufferedJoinExec.nextRows:185-264 for unique build keys, no NULLs)
+    unsigned int my_total = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        int64_t r = t0 + k * THREADS + threadIdx.x;
+        bool live = r < n;
+        bool emit;
+        switch (O.join_type) {
+        case GSQL_JOIN_INNER: emit = found[k]; break;
+        case GSQL_JOIN_SEMI: emit = found[k]; break;
+        case GSQL_JOIN_ANTI: emit = !found[k]; break;
+        default: emit = true; break;  // LEFT / RIGHT: unmatched probe rows are NULL-padded
+        }
+        emit = emit && live;
+        ballot[k] = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) cell[warp][k] = __popc(ballot[k]);
+        my_total += emit;
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan over the 64 (warp, k) cells + one cursor bump for the tile
+        constexpr int CELLS = (THREADS / 32) * RPT;
+        unsigned int *flat = &cell[0][0];
+        unsigned int a = flat[lane * 2], b = flat[lane * 2 + 1];
+        unsigned int sum = a + b, incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        unsigned int excl = incl - sum;
+        unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) tile_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+        flat[lane * 2] = excl;
+        flat[lane * 2 + 1] = excl + a;
+        static_assert(CELLS == 64, "cell scan assumes 64 cells");
+    }
+    __syncthreads();
+    // 4. write the output columns: consecutive lanes -> consecutive positions (coalesced, evict-first)
+    const unsigned long long base = tile_base;
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        if (!((ballot[k] >> lane) & 1u)) continue;
+        unsigned long long pos = base + cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+#pragma unroll 1
+        for (int q = 0; q < O.nout; q++) {
+            unsigned long long v;
+            bool isnull = false;
+            if (O.side[q] == 0) {
+                v = pick<PW>(pw[k], O.word[q]);
+            } else {
+                isnull = !found[k];
+                v = O.word[q] == 0 ? pw[k][0] : pick<BP>(bp[k], O.word[q] - 1);
+            }
+            if (O.half[q] == 1) v >>= 32;
+            if (O.nulls[q]) O.nulls[q][pos] = isnull ? 1 : 0;
+            else if (isnull) flags[FL_NULLOUT] = 1;
+            if (isnull) v = 0;
+            if (O.is32[q]) st_stream_4(reinterpret_cast<int *>(O.data[q]) + pos, (int)(unsigned)v);
+            else st_stream_8(reinterpret_cast<long long *>(O.data[q]) + pos, (long long)v);
+        }
+    }
+}
+
+}  // namespace fj
+
 struct JoinFast {
-    bool enabled = false;
+    bool eligible = false;   // decided at create: shape supports the packed single-key path
+    bool enabled = false;    // table built and usable
+    fj::Layout bl, pl;       // build / probe packed-row layouts
+    int P = 1;               // partitions (1 = table small enough to stay in L2 without partitioning)
+    uint64_t nslots = 0;
+    DevBuf table, flags, cursor;
+    int64_t part_bytes = 32ll << 20;
+    int64_t sub_batch = 256ll << 20;  // probe rows per partition+probe round (bounds scratch memory)
 };

@@ -131,7 +131,7 @@ def test_join_heavy_duplicates(gu):
     spec = orc.JoinSpec(orc.JOIN_INNER, [0], [0], [orc.T_INT64])
     exp = orc.hash_join(spec, outer, inner)
     got = gu.gpu_hash_join(spec, outer, inner, mem="device")
-    assert len(got[0][0]) == len(exp[0][0]) == 30 * 3000 + 30 * 1
+    assert len(got[0][0]) == len(exp[0][0]) == 30 * 3001 + 4 * 30     # key 7: 3000 even rows + row 7; keys 1,3,5,9 once
     assert ku.rows_multiset(got) == ku.rows_multiset(exp)
 
 
@@ -158,6 +158,74 @@ def test_join_c2_shape_scaled(gu):
     sl = slice(0, 1_000_000)
     o2 = [(d[sl], None) for d, _ in outer]
     assert ku.rows_multiset(gu.gpu_hash_join(spec, o2, inner, mem="device")) == ku.rows_multiset(orc.hash_join(spec, o2, inner))
+
+
+# ------------------------------------------------------------------------------------------------ fast (partitioned) join path
+@pytest.fixture
+def small_partitions(monkeypatch):
+    """Force the radix-partitioned path (P > 1, several sub-batches) at test sizes."""
+    monkeypatch.setenv("GSQL_JOIN_PART_BYTES", str(64 << 10))
+    monkeypatch.setenv("GSQL_JOIN_SUB_BATCH", "30000")
+
+
+def _unique_key_tables(nb, npr, key_space, key_dtype, n_build_pay, n_probe_pay, seed):
+    perm = np.argsort(ku.rand_u64(key_space, seed))[:nb].astype(key_dtype)
+    if key_dtype == np.int64:
+        perm = perm * 1_000_003 - 7_000_000_000          # spread over 64-bit, includes negatives
+    else:
+        perm = perm - key_space // 2
+    pk = perm[(ku.rand_u64(npr, seed + 1) % np.uint64(nb)).astype(np.int64)].copy()
+    miss = (ku.rand_u64(npr, seed + 2) % np.uint64(4)) == 0           # ~25 % of probe keys have no partner
+    pk[miss] = pk[miss] + (1 if key_dtype == np.int32 else 1)
+    pay_types = [np.int32, np.int64, np.float64, np.int32, np.int32]
+    def pays(n, k, s0):
+        out = []
+        for i in range(k):
+            v = (ku.rand_u64(n, s0 + i) % np.uint64(1 << 30))
+            out.append((v.astype(pay_types[i]), None))
+        return out
+    inner = [(perm, None)] + pays(nb, n_build_pay, seed + 10)
+    outer = pays(npr, n_probe_pay, seed + 20)
+    outer.insert(min(1, len(outer)), (pk, None))                       # key column not always first
+    return outer, inner, min(1, n_probe_pay)
+
+
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_RIGHT, orc.JOIN_SEMI, orc.JOIN_ANTI])
+@pytest.mark.parametrize("shape", [(np.int64, 2, 2), (np.int32, 0, 1), (np.int64, 3, 0), (np.int32, 5, 4), (np.int64, 1, 3)])
+def test_fast_join_partitioned_vs_oracle(gu, small_partitions, jt, shape):
+    key_dtype, nbp, npp = shape
+    outer, inner, kc = _unique_key_tables(40_000, 100_000, 60_000, key_dtype, nbp, npp, seed=900 + jt)
+    kt = orc.T_INT64 if key_dtype == np.int64 else orc.T_INT32
+    spec = orc.JoinSpec(jt, [kc], [0], [kt])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    got = ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="device", build_batches=2))
+    assert got == exp
+    got_h = ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="host"))
+    assert got_h == exp
+
+
+def test_fast_join_is_taken_and_falls_back(gu, small_partitions):
+    from galaxysql_b200 import api, native as N
+    outer, inner, kc = _unique_key_tables(40_000, 50_000, 60_000, np.int64, 2, 2, seed=77)
+    j = api.HashJoin(gu.ctx(), N.JOIN_INNER, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    j.build_consume(inner)
+    j.build_finish()
+    info = j.info()
+    assert info.fast_path == 1 and info.partitions > 1
+    spec = orc.JoinSpec(orc.JOIN_INNER, [kc], [0], [orc.T_INT64])
+    assert ku.rows_multiset(gu.to_numpy(j.probe(outer))) == ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    # a probe batch with NULLs is not packed: the same handle answers through the generic table
+    outer_n = [ku.with_nulls(outer[0][0], 0.05, 5), ku.with_nulls(outer[1][0], 0.05, 6), outer[2]]
+    assert ku.rows_multiset(gu.to_numpy(j.probe(outer_n))) == ku.rows_multiset(orc.hash_join(spec, outer_n, inner))
+    j.close()
+    # duplicate build keys disable the fast table altogether
+    inner_d = [(np.concatenate([inner[0][0], inner[0][0][:10]]), None)] + [(np.concatenate([c[0], c[0][:10]]), None) for c in inner[1:]]
+    j = api.HashJoin(gu.ctx(), N.JOIN_INNER, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    j.build_consume(inner_d)
+    j.build_finish()
+    assert j.info().fast_path == 0 and j.info().has_duplicate_keys == 1
+    assert ku.rows_multiset(gu.to_numpy(j.probe(outer))) == ku.rows_multiset(orc.hash_join(spec, outer, inner_d))
+    j.close()
 
 
 # ------------------------------------------------------------------------------------------------ aggregation

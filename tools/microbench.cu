@@ -78,6 +78,14 @@ __global__ void k_fill(int4 *p, size_t n, unsigned mod) {
     }
 }
 
+__global__ void k_cursor(unsigned long long *cur, size_t nops, int per_warp) {
+    // one lane per warp (or per block) bumps a single global cursor, like a tile-level output reservation
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < nops * 32; i += stride)
+        if ((threadIdx.x & 31) == 0 && (per_warp || threadIdx.x == 0)) atomicAdd(cur, 7ULL);
+}
+
 static float timeit(void (*launch)(void *), void *arg, int reps) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     launch(arg); CK(cudaDeviceSynchronize());
@@ -132,6 +140,18 @@ int main() {
         a.nslots = (uint64_t)1 << lg; a.nprobe = (size_t)1 << 27;
         float ms = timeit(l_at, &a, 3);
         printf("atomicAdd(double) table %9.3f MiB: %.2f Gops/s\n", (double)(a.nslots * 8) / 1048576.0, a.nprobe / ms / 1e6);
+    }
+    {
+        unsigned long long *cur; CK(cudaMalloc(&cur, 8)); CK(cudaMemset(cur, 0, 8));
+        for (int pw = 1; pw >= 0; pw--) {
+            size_t nops = (size_t)1 << 22;
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            k_cursor<<<sms * 8, 256>>>(cur, nops, pw); CK(cudaDeviceSynchronize());
+            cudaEventRecord(e0); k_cursor<<<sms * 8, 256>>>(cur, nops, pw); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double n = pw ? (double)nops : (double)nops / 8;
+            printf("single-address atomicAdd(u64), one lane per %s: %.1f Mops/s (%.3f ms for %.0f ops)\n", pw ? "warp" : "block", n / ms / 1e3, ms, n);
+        }
     }
     return 0;
 }
