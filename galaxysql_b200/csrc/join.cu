@@ -845,85 +845,210 @@ gsql_status download_outputs(gsql_join *j, gsql_batch *out, int64_t rows, const 
     return GSQL_OK;
 }
 
-// Probe through the packed single-key table.  *handled = false leaves the batch to the generic path.
-static gsql_status fast_probe(gsql_join *j, const StagedBatch &sp, const gsql_batch *probe, gsql_batch *out, int64_t out_capacity,
-                              int64_t *out_rows, bool *handled) {
-    *handled = false;
+
+static void fast_out_map(gsql_join *j, const ProbeParams &PP, fj::OutMap *O) {
+    JoinFast &F = j->fast;
+    memset(O, 0, sizeof(*O));
+    O->nout = j->nout;
+    O->join_type = j->spec.join_type;
+    for (int q = 0; q < j->nout; q++) {
+        const fj::Layout &L = j->out_side[q] == SIDE_PROBE ? F.pl : F.bl;
+        O->data[q] = PP.out[q].data;
+        O->nulls[q] = PP.out[q].nulls;
+        O->side[q] = (int8_t)(j->out_side[q] == SIDE_PROBE ? 0 : 1);
+        O->word[q] = (int8_t)L.word[j->out_col[q]];
+        O->half[q] = (int8_t)L.half[j->out_col[q]];
+        O->is32[q] = (int8_t)(j->out_types[q] == GSQL_T_INT32);
+    }
+}
+
+// Partition (when P > 1) + probe of `m` device-resident rows; output rows are appended at *cursor.
+static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m, unsigned long long *packed, const fj::OutMap &O,
+                                   unsigned long long *cursor) {
     JoinFast &F = j->fast;
     gsql_ctx *ctx = j->ctx;
-    if (!F.enabled) return GSQL_OK;
-    const int64_t n = sp.rows;
-    if (out_capacity < n) return GSQL_OK;  // <= 1 output row per probe row; smaller buffers take the exact two-pass path
-    for (int i = 0; i < sp.ncols; i++)
-        if (probe->cols[i].nulls) return GSQL_OK;
-    const int jt = j->spec.join_type;
+    const int PW = F.pl.nwords, BW = F.bl.nwords;
+    const unsigned long long *src = nullptr;
+    if (F.P > 1) {
+        GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed, F.flags.as<int32_t>(), "probe"));
+        src = packed;
+    }
+    {
+        KernelScope ks(ctx, "join_fast_probe");
+        int grid = (int)div_up(m, fj::TILE);
+#define FJ_PROBE_CASE(PWv, BWv)                                                                                                         \
+    if (PW == PWv && BW == BWv)                                                                                                         \
+        fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, 0, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
+                                                                       cursor, F.flags.as<int32_t>());
+        FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
+        FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
+        FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
+        FJ_PROBE_CASE(4, 1) FJ_PROBE_CASE(4, 2) FJ_PROBE_CASE(4, 3) FJ_PROBE_CASE(4, 4)
+#undef FJ_PROBE_CASE
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    return GSQL_OK;
+}
+
+static bool fast_probe_applicable(gsql_join *j, const gsql_batch *probe, const gsql_batch *out, int64_t out_capacity, gsql_status *err) {
+    *err = GSQL_OK;
+    if (!j->fast.enabled) return false;
+    if (out_capacity < probe->rows) return false;  // <= 1 output row per probe row; smaller buffers take the exact two-pass path
+    for (int i = 0; i < probe->ncols; i++)
+        if (probe->cols[i].nulls) return false;
     if (j->outer_join)
         for (int q = 0; q < j->nout; q++)
-            if (j->out_side[q] == SIDE_BUILD && !out->cols[q].nulls)
-                return gsql_set_error(ctx, GSQL_E_INVALID, "outer join: output column %d needs a nulls buffer", q);
+            if (j->out_side[q] == SIDE_BUILD && !out->cols[q].nulls) {
+                *err = gsql_set_error(j->ctx, GSQL_E_INVALID, "outer join: output column %d needs a nulls buffer", q);
+                return false;
+            }
+    return true;
+}
+
+static gsql_status fast_check_flags(gsql_join *j) {
+    gsql_ctx *ctx = j->ctx;
+    int32_t hf[fj::FL_COUNT];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hf, j->fast.flags.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hf[fj::FL_NULLOUT]) {
+        cudaMemsetAsync(j->fast.flags.p, 0, fj::FL_COUNT * 4, ctx->stream);
+        return gsql_set_error(ctx, GSQL_E_INVALID, "a NULL had to be written into an output column without a nulls buffer");
+    }
+    return GSQL_OK;
+}
+
+// Host batches: software pipeline over slices — H2D of slice i+1 (copy-in stream), partition+probe of slice i (compute
+// stream) and D2H of slice i-1's output (copy-out stream) overlap, so the call is bound by max(PCIe in, PCIe out).
+static gsql_status fast_probe_host(gsql_join *j, const gsql_batch *probe, gsql_batch *out, int64_t *out_rows) {
+    JoinFast &F = j->fast;
+    gsql_ctx *ctx = j->ctx;
+    const int64_t n = probe->rows;
+    int64_t S = env_i64("GSQL_JOIN_HOST_SLICE", 16ll << 20);
+    if (S < fj::TILE) S = fj::TILE;
+    if (S > n) S = n;
+    const int nsl = (int)div_up(n, S);
+    const int nc = probe->ncols, no = j->nout;
+    const int PW = F.pl.nwords;
+    std::vector<DevBuf> in((size_t)2 * nc), od((size_t)2 * no), on((size_t)2 * no);
+    DevBuf packed, cursors;
+    for (int b = 0; b < 2; b++) {
+        for (int c = 0; c < nc; c++) GSQL_TRY(in[(size_t)b * nc + c].alloc(ctx, (size_t)S * gsql_type_width(j->probe_types[c])));
+        for (int q = 0; q < no; q++) {
+            GSQL_TRY(od[(size_t)b * no + q].alloc(ctx, (size_t)S * gsql_type_width(j->out_types[q])));
+            if (out->cols[q].nulls) GSQL_TRY(on[(size_t)b * no + q].alloc(ctx, (size_t)S));
+        }
+    }
+    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)S * PW * 8));
+    GSQL_TRY(cursors.alloc(ctx, (size_t)nsl * 8));
+    GSQL_CUDA(ctx, cudaMemsetAsync(cursors.p, 0, (size_t)nsl * 8, ctx->stream));
+    unsigned long long *hcount = nullptr;
+    GSQL_CUDA(ctx, cudaHostAlloc((void **)&hcount, (size_t)nsl * 8, cudaHostAllocDefault));
+    std::vector<cudaEvent_t> in_done((size_t)nsl), comp_done((size_t)nsl), d2h_done((size_t)nsl);
+    for (int i = 0; i < nsl; i++) {
+        cudaEventCreateWithFlags(&in_done[(size_t)i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&comp_done[(size_t)i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&d2h_done[(size_t)i], cudaEventDisableTiming);
+    }
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // buffers exist before the copy streams touch them
+    gsql_status st = GSQL_OK;
+    int64_t host_off = 0;
+    auto drain = [&](int i) -> gsql_status {  // stage C for slice i
+        GSQL_CUDA(ctx, cudaEventSynchronize(comp_done[(size_t)i]));
+        int64_t cnt = (int64_t)hcount[i];
+        int b = i & 1;
+        for (int q = 0; q < no; q++) {
+            size_t w = (size_t)gsql_type_width(j->out_types[q]);
+            if (cnt > 0) {
+                GSQL_CUDA(ctx, cudaMemcpyAsync((char *)out->cols[q].data + (size_t)host_off * w, od[(size_t)b * no + q].p, (size_t)cnt * w, cudaMemcpyDeviceToHost, ctx->copy_out));
+                if (out->cols[q].nulls)
+                    GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[q].nulls + host_off, on[(size_t)b * no + q].p, (size_t)cnt, cudaMemcpyDeviceToHost, ctx->copy_out));
+            }
+        }
+        GSQL_CUDA(ctx, cudaEventRecord(d2h_done[(size_t)i], ctx->copy_out));
+        host_off += cnt;
+        return GSQL_OK;
+    };
+    for (int i = 0; i < nsl && st == GSQL_OK; i++) {
+        const int b = i & 1;
+        const int64_t lo = (int64_t)i * S, m = n - lo < S ? n - lo : S;
+        // A: H2D of slice i (its buffer is free once slice i-2 has been computed)
+        if (i >= 2) cudaStreamWaitEvent(ctx->copy_in, comp_done[(size_t)i - 2], 0);
+        DColSet cols;
+        memset(&cols, 0, sizeof(cols));
+        cols.n = nc;
+        for (int c = 0; c < nc && st == GSQL_OK; c++) {
+            size_t w = (size_t)gsql_type_width(j->probe_types[c]);
+            if (cudaMemcpyAsync(in[(size_t)b * nc + c].p, (const char *)probe->cols[c].data + (size_t)lo * w, (size_t)m * w, cudaMemcpyHostToDevice, ctx->copy_in) != cudaSuccess)
+                st = gsql_set_error(ctx, GSQL_E_CUDA, "H2D slice copy failed");
+            cols.c[c].data = in[(size_t)b * nc + c].p;
+            cols.c[c].nulls = nullptr;
+            cols.c[c].type = j->probe_types[c];
+        }
+        cudaEventRecord(in_done[(size_t)i], ctx->copy_in);
+        // B: partition + probe of slice i
+        cudaStreamWaitEvent(ctx->stream, in_done[(size_t)i], 0);
+        if (i >= 2) cudaStreamWaitEvent(ctx->stream, d2h_done[(size_t)i - 2], 0);
+        ProbeParams PP;
+        memset(&PP, 0, sizeof(PP));
+        for (int q = 0; q < no; q++) {
+            PP.out[q].data = od[(size_t)b * no + q].p;
+            PP.out[q].nulls = out->cols[q].nulls ? on[(size_t)b * no + q].as<uint8_t>() : nullptr;
+        }
+        fj::OutMap O;
+        fast_out_map(j, PP, &O);
+        if (st == GSQL_OK) st = fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, cursors.as<unsigned long long>() + i);
+        cudaMemcpyAsync(&hcount[i], cursors.as<unsigned long long>() + i, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(comp_done[(size_t)i], ctx->stream);
+        // C: D2H of slice i-1's output
+        if (i >= 1 && st == GSQL_OK) st = drain(i - 1);
+    }
+    if (st == GSQL_OK) st = drain(nsl - 1);
+    cudaStreamSynchronize(ctx->copy_in);
+    cudaStreamSynchronize(ctx->copy_out);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < nsl; i++) {
+        cudaEventDestroy(in_done[(size_t)i]);
+        cudaEventDestroy(comp_done[(size_t)i]);
+        cudaEventDestroy(d2h_done[(size_t)i]);
+    }
+    cudaFreeHost(hcount);
+    if (st != GSQL_OK) return st;
+    GSQL_TRY(fast_check_flags(j));
+    *out_rows = out->rows = host_off;
+    return GSQL_OK;
+}
+
+// Device-resident (or already staged) batch through the packed single-key table.
+static gsql_status fast_probe(gsql_join *j, const StagedBatch &sp, gsql_batch *out, int64_t *out_rows) {
+    JoinFast &F = j->fast;
+    gsql_ctx *ctx = j->ctx;
+    const int64_t n = sp.rows;
     ProbeWork w;
     ProbeParams PP;
     GSQL_TRY(fill_params(j, sp, &PP));
     GSQL_TRY(bind_outputs(j, out, n, &PP, &w));
     fj::OutMap O;
-    memset(&O, 0, sizeof(O));
-    O.nout = j->nout;
-    O.join_type = jt;
-    for (int q = 0; q < j->nout; q++) {
-        const fj::Layout &L = j->out_side[q] == SIDE_PROBE ? F.pl : F.bl;
-        O.data[q] = PP.out[q].data;
-        O.nulls[q] = PP.out[q].nulls;
-        O.side[q] = (int8_t)(j->out_side[q] == SIDE_PROBE ? 0 : 1);
-        O.word[q] = (int8_t)L.word[j->out_col[q]];
-        O.half[q] = (int8_t)L.half[j->out_col[q]];
-        O.is32[q] = (int8_t)(j->out_types[q] == GSQL_T_INT32);
-    }
+    fast_out_map(j, PP, &O);
     GSQL_CUDA(ctx, cudaMemsetAsync(F.cursor.p, 0, 16, ctx->stream));
-    const int PW = F.pl.nwords, BW = F.bl.nwords;
     DColSet cols;
     memset(&cols, 0, sizeof(cols));
     cols.n = sp.ncols;
     DevBuf packed;
     const int64_t sub = F.P > 1 ? (F.sub_batch < n ? F.sub_batch : n) : n;
-    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)sub * PW * 8));
+    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)sub * F.pl.nwords * 8));
     for (int64_t lo = 0; lo < n; lo += sub) {
         int64_t m = n - lo < sub ? n - lo : sub;
         for (int i = 0; i < sp.ncols; i++) {
             cols.c[i] = sp.cols[i];
             cols.c[i].data = (const char *)sp.cols[i].data + (size_t)lo * gsql_type_width(sp.cols[i].type);
         }
-        const unsigned long long *src = nullptr;
-        if (F.P > 1) {
-            GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed.as<unsigned long long>(), F.flags.as<int32_t>(), "probe"));
-            src = packed.as<unsigned long long>();
-        }
-        {
-            KernelScope ks(ctx, "join_fast_probe");
-            int grid = (int)div_up(m, fj::TILE);
-#define FJ_PROBE_CASE(PWv, BWv)                                                                                                         \
-    if (PW == PWv && BW == BWv)                                                                                                         \
-        fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, 0, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
-                                                                       F.cursor.as<unsigned long long>(), F.flags.as<int32_t>());
-            FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
-            FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
-            FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
-            FJ_PROBE_CASE(4, 1) FJ_PROBE_CASE(4, 2) FJ_PROBE_CASE(4, 3) FJ_PROBE_CASE(4, 4)
-#undef FJ_PROBE_CASE
-        }
-        GSQL_CUDA(ctx, cudaGetLastError());
+        GSQL_TRY(fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, F.cursor.as<unsigned long long>()));
     }
     unsigned long long total = 0;
-    int32_t hf[fj::FL_COUNT];
     GSQL_CUDA(ctx, cudaMemcpyAsync(&total, F.cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    GSQL_CUDA(ctx, cudaMemcpyAsync(hf, F.flags.p, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
-    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (hf[fj::FL_NULLOUT]) {
-        cudaMemsetAsync(F.flags.p, 0, fj::FL_COUNT * 4, ctx->stream);
-        return gsql_set_error(ctx, GSQL_E_INVALID, "a NULL had to be written into an output column without a nulls buffer");
-    }
+    GSQL_TRY(fast_check_flags(j));
     GSQL_TRY(download_outputs(j, out, (int64_t)total, PP));
     *out_rows = out->rows = (int64_t)total;
-    *handled = true;
     return GSQL_OK;
 }
 
@@ -980,11 +1105,13 @@ extern "C" gsql_status gsql_join_probe(gsql_join *j, const gsql_batch *probe, gs
         return GSQL_OK;
     }
     ProbeWork w;
-    GSQL_TRY(stage_batch(ctx, probe, &w.probe));
-    if (j->fast.enabled) {
-        bool handled = false;
-        GSQL_TRY(fast_probe(j, w.probe, probe, out, out_capacity, out_rows, &handled));
-        if (handled) return GSQL_OK;
+    {
+        gsql_status ferr = GSQL_OK;
+        bool fast = fast_probe_applicable(j, probe, out, out_capacity, &ferr);
+        if (ferr != GSQL_OK) return ferr;
+        if (fast && probe->mem == GSQL_MEM_HOST && probe->rows >= (1 << 20)) return fast_probe_host(j, probe, out, out_rows);
+        GSQL_TRY(stage_batch(ctx, probe, &w.probe));
+        if (fast) return fast_probe(j, w.probe, out, out_rows);
     }
     GSQL_TRY(ensure_generic(j));
     ProbeParams P;

@@ -98,6 +98,44 @@ __device__ __forceinline__ void pack_row(const DColSet &cols, const Layout &L, i
     }
 }
 
+// Packs the RPT rows a thread owns in a tile (rows base + k*THREADS).  Column loop outside, row loop inside and
+// unrolled: RPT independent coalesced loads are in flight per column instead of one dependent load at a time.
+template <int W>
+__device__ __forceinline__ void pack_tile(const DColSet &cols, const Layout &L, int64_t base, int64_t limit, unsigned long long (&w)[RPT][W]) {
+#pragma unroll
+    for (int k = 0; k < RPT; k++)
+#pragma unroll
+        for (int i = 0; i < W; i++) w[k][i] = 0;
+#pragma unroll 1
+    for (int c = 0; c < L.ncols; c++) {
+        const DCol &col = cols.c[c];
+        const bool is32 = col.type == GSQL_T_INT32, iskey = c == L.key_col;
+        const int wi = L.word[c];
+        const int sh = L.half[c] == 1 ? 32 : 0;
+        unsigned long long v[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = base + k * THREADS;
+            v[k] = 0;
+            if (r < limit) {
+                if (is32) {
+                    int x = ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
+                    v[k] = iskey ? (unsigned long long)(long long)x : (unsigned long long)(unsigned)x;
+                } else {
+                    v[k] = (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            unsigned long long vv = v[k] << sh;
+#pragma unroll
+            for (int i = 0; i < W; i++)
+                if (i == wi) w[k][i] |= vv;
+        }
+    }
+}
+
 __device__ __forceinline__ unsigned long long load_key(const DCol &col, int64_t r) {
     if (col.type == GSQL_T_INT32) return (unsigned long long)(long long)ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
     return (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
@@ -116,10 +154,21 @@ __global__ void __launch_bounds__(THREADS) k_fj_hist(DCol keycol, PartGeom g, in
     int64_t r0 = (int64_t)blockIdx.x * g.chunk;
     int64_t r1 = r0 + g.chunk < g.rows ? r0 + g.chunk : g.rows;
     bool sentinel = false;
-    for (int64_t r = r0 + threadIdx.x; r < r1; r += THREADS) {
-        unsigned long long k = load_key(keycol, r);
-        sentinel |= k == KEY_EMPTY;
-        atomicAdd(&sh_hist[(unsigned)__umul64hi(key_hash(k), (uint64_t)g.P)], 1u);
+    for (int64_t t0 = r0; t0 < r1; t0 += TILE) {
+        unsigned long long key[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            key[k] = r < r1 ? load_key(keycol, r) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            if (r < r1) {
+                sentinel |= key[k] == KEY_EMPTY;
+                atomicAdd(&sh_hist[(unsigned)__umul64hi(key_hash(key[k]), (uint64_t)g.P)], 1u);
+            }
+        }
     }
     if (sentinel) flags[FL_SENTINEL] = 1;
     __syncthreads();
@@ -149,12 +198,12 @@ __global__ void __launch_bounds__(THREADS) k_fj_scatter(const __grid_constant__ 
     for (int64_t t0 = r0; t0 < r1; t0 += TILE) {
         unsigned long long w[RPT][W];
         unsigned int pid[RPT], rank[RPT];
+        pack_tile<W>(cols, L, t0 + threadIdx.x, r1, w);
 #pragma unroll
         for (int k = 0; k < RPT; k++) {
             int64_t r = t0 + k * THREADS + threadIdx.x;
             pid[k] = 0xffffffffu;
             if (r < r1) {
-                pack_row<W>(cols, L, r, w[k]);
                 pid[k] = (unsigned)__umul64hi(key_hash(w[k][0]), (uint64_t)g.P);
                 rank[k] = atomicAdd(&hist[pid[k]], 1u);
             }
@@ -225,35 +274,46 @@ __global__ void __launch_bounds__(THREADS) k_fj_insert(const unsigned long long 
                                                        const __grid_constant__ Layout L, int64_t n, unsigned long long *table, uint64_t nslots,
                                                        int32_t *flags) {
     for (int64_t t0 = (int64_t)blockIdx.x * TILE; t0 < n; t0 += (int64_t)gridDim.x * TILE) {
-#pragma unroll 1
+        unsigned long long w[RPT][W];
+        if (packed) {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                int64_t r = t0 + k * THREADS + threadIdx.x;
+#pragma unroll
+                for (int i = 0; i < W; i++) w[k][i] = r < n ? (unsigned long long)ld_stream_8(packed + r * W + i) : 0;
+            }
+        } else {
+            pack_tile<W>(cols, L, t0 + threadIdx.x, n, w);
+        }
+        // first attempt for all RPT rows at once (at load <= 0.5 most land in an empty slot), then the stragglers
+        uint64_t s[RPT];
+        unsigned long long prev[RPT];
+#pragma unroll
         for (int k = 0; k < RPT; k++) {
             int64_t r = t0 + k * THREADS + threadIdx.x;
-            if (r >= n) break;
-            unsigned long long w[W];
-            if (packed) {
-#pragma unroll
-                for (int i = 0; i < W; i++) w[i] = (unsigned long long)ld_stream_8(packed + r * W + i);
-            } else {
-                pack_row<W>(cols, L, r, w);
+            s[k] = __umul64hi(key_hash(w[k][0]), nslots);
+            prev[k] = 1;  // "not attempted"
+            if (r < n) {
+                if (w[k][0] == KEY_EMPTY) flags[FL_SENTINEL] = 1;
+                else prev[k] = atomicCAS(table + s[k] * W, KEY_EMPTY, w[k][0]);
             }
-            if (w[0] == KEY_EMPTY) { flags[FL_SENTINEL] = 1; continue; }
-            uint64_t s = __umul64hi(key_hash(w[0]), nslots);
-            int disp = 0;
-            while (true) {
-                unsigned long long *slot = table + s * W;
-                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(slot);
-                if (cur == KEY_EMPTY) {
-                    unsigned long long prev = atomicCAS(slot, KEY_EMPTY, w[0]);
-                    if (prev == KEY_EMPTY) {
+        }
 #pragma unroll
-                        for (int i = 1; i < W; i++) slot[i] = w[i];
-                        break;
-                    }
-                    cur = prev;
-                }
-                if (cur == w[0]) { flags[FL_DUP] = 1; break; }  // duplicate build key: the generic (chained) path takes over
-                if (++s == nslots) s = 0;
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            if (r >= n || w[k][0] == KEY_EMPTY) continue;
+            unsigned long long p = prev[k];
+            uint64_t sl = s[k];
+            int disp = 0;
+            while (p != KEY_EMPTY) {
+                if (p == w[k][0]) { flags[FL_DUP] = 1; break; }  // duplicate build key: the generic (chained) path takes over
+                if (++sl == nslots) sl = 0;
                 if (++disp > MAX_DISP) { flags[FL_DISP] = 1; break; }
+                p = atomicCAS(table + sl * W, KEY_EMPTY, w[k][0]);
+            }
+            if (p == KEY_EMPTY) {
+#pragma unroll
+                for (int i = 1; i < W; i++) table[sl * W + i] = w[k][i];
             }
         }
     }
@@ -297,12 +357,12 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
     bool found[RPT];
     uint64_t slot[RPT];
 
-    // 1. stream the probe rows in
+    // 1. stream the probe rows in (all RPT loads in flight)
+    if (packed) {
 #pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        int64_t r = t0 + k * THREADS + threadIdx.x;
-        if (r < n) {
-            if (packed) {
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = t0 + k * THREADS + threadIdx.x;
+            if (r < n) {
                 if (PW == 2) {
                     int4 v = ld_stream_16(packed + r * 2);
                     pw[k][0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
@@ -312,27 +372,40 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
                     for (int i = 0; i < PW; i++) pw[k][i] = (unsigned long long)ld_stream_8(packed + r * PW + i);
                 }
             } else {
-                pack_row<PW>(cols, L, r, pw[k]);
-            }
-            slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
-        } else {
 #pragma unroll
-            for (int i = 0; i < PW; i++) pw[k][i] = 0;
-            pw[k][0] = KEY_EMPTY;
-            slot[k] = 0;
+                for (int i = 0; i < PW; i++) pw[k][i] = 0;
+            }
         }
+    } else {
+        pack_tile<PW>(cols, L, t0 + threadIdx.x, n, pw);
     }
-    // 2. one L2-resident table read per row (all RPT reads in flight), then the rare collision walks
+    // 2. one L2-resident table read per row, all RPT reads issued before any is consumed; then the rare walks.
+    //    A key equal to KEY_EMPTY (padding rows, and the one value the fast table never holds) cannot match.
+    unsigned long long tkey[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
-        found[k] = false;
+        int64_t r = t0 + k * THREADS + threadIdx.x;
+        if (r >= n) pw[k][0] = KEY_EMPTY;
+        slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
 #pragma unroll
         for (int i = 0; i < BP; i++) bp[k][i] = 0;
+        if (BW == 2) {
+            int4 v = ld_keep_16(table + slot[k] * 2, pol);
+            tkey[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+            bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+        } else {
+            tkey[k] = ld_keep_8(table + slot[k] * BW, pol);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
         unsigned long long key = pw[k][0];
-        if (key == KEY_EMPTY) continue;  // padding rows, and the one key value the fast table cannot hold (never built)
+        unsigned long long tk = tkey[k];
         uint64_t s = slot[k];
-        while (true) {
-            unsigned long long tk;
+        found[k] = false;
+        if (key == KEY_EMPTY) continue;
+        while (tk != key && tk != KEY_EMPTY) {  // linear probing past other keys
+            if (++s == nslots) s = 0;
             if (BW == 2) {
                 int4 v = ld_keep_16(table + s * 2, pol);
                 tk = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
@@ -340,16 +413,13 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
             } else {
                 tk = ld_keep_8(table + s * BW, pol);
             }
-            if (tk == key) {
-                if (BW > 2) {
+        }
+        if (tk == key) {
+            found[k] = true;
+            if (BW > 2) {
 #pragma unroll
-                    for (int i = 1; i < BW; i++) bp[k][i - 1] = ld_keep_8(table + s * BW + i, pol);
-                }
-                found[k] = true;
-                break;
+                for (int i = 1; i < BW; i++) bp[k][i - 1] = ld_keep_8(table + s * BW + i, pol);
             }
-            if (tk == KEY_EMPTY) break;
-            if (++s == nslots) s = 0;
         }
     }
     // 3. which rows emit (AbstractBufferedJoinExec.nextRows:185-264 for unique build keys, no NULLs)

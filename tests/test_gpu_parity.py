@@ -204,6 +204,17 @@ def test_fast_join_partitioned_vs_oracle(gu, small_partitions, jt, shape):
     assert got_h == exp
 
 
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_ANTI])
+def test_fast_join_host_pipeline(gu, monkeypatch, jt):
+    """Host batches >= 1M rows go through the sliced H2D / compute / D2H pipeline (5 slices here)."""
+    monkeypatch.setenv("GSQL_JOIN_PART_BYTES", str(256 << 10))
+    monkeypatch.setenv("GSQL_JOIN_HOST_SLICE", "300000")
+    outer, inner, kc = _unique_key_tables(100_000, 1_300_000, 150_000, np.int64, 2, 2, seed=1200 + jt)
+    spec = orc.JoinSpec(jt, [kc], [0], [orc.T_INT64])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="host")) == exp
+
+
 def test_fast_join_is_taken_and_falls_back(gu, small_partitions):
     from galaxysql_b200 import api, native as N
     outer, inner, kc = _unique_key_tables(40_000, 50_000, 60_000, np.int64, 2, 2, seed=77)
