@@ -873,7 +873,26 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed, F.flags.as<int32_t>(), "probe"));
         src = packed;
     }
-    {
+    if (src && !env_i64("GSQL_JOIN_NO_TMA", 0)) {  // packed rows: TMA-staged persistent kernel
+        KernelScope ks(ctx, "join_fast_probe");
+        size_t smem = fj::probe_tma_smem_bytes(PW);
+        int64_t ntiles = div_up(m, fj::PT_TILE);
+        int per_sm = (int)(220 * 1024 / (smem + 1024));
+        if (per_sm > 3) per_sm = 3;
+        if (per_sm < 1) per_sm = 1;
+        int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
+#define FJ_PROBE_CASE(PWv, BWv)                                                                                                              \
+    if (PW == PWv && BW == BWv) {                                                                                                            \
+        GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
+                                                                               F.flags.as<int32_t>());                                       \
+    }
+        FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
+        FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
+        FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
+        FJ_PROBE_CASE(4, 1) FJ_PROBE_CASE(4, 2) FJ_PROBE_CASE(4, 3) FJ_PROBE_CASE(4, 4)
+#undef FJ_PROBE_CASE
+    } else {
         KernelScope ks(ctx, "join_fast_probe");
         int grid = (int)div_up(m, fj::TILE);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                         \
@@ -938,7 +957,7 @@ static gsql_status fast_probe_host(gsql_join *j, const gsql_batch *probe, gsql_b
             if (out->cols[q].nulls) GSQL_TRY(on[(size_t)b * no + q].alloc(ctx, (size_t)S));
         }
     }
-    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)S * PW * 8));
+    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)S * PW * 8 + 64));
     GSQL_TRY(cursors.alloc(ctx, (size_t)nsl * 8));
     GSQL_CUDA(ctx, cudaMemsetAsync(cursors.p, 0, (size_t)nsl * 8, ctx->stream));
     unsigned long long *hcount = nullptr;
@@ -1035,7 +1054,7 @@ static gsql_status fast_probe(gsql_join *j, const StagedBatch &sp, gsql_batch *o
     cols.n = sp.ncols;
     DevBuf packed;
     const int64_t sub = F.P > 1 ? (F.sub_batch < n ? F.sub_batch : n) : n;
-    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)sub * F.pl.nwords * 8));
+    if (F.P > 1) GSQL_TRY(packed.alloc(ctx, (size_t)sub * F.pl.nwords * 8 + 64));
     for (int64_t lo = 0; lo < n; lo += sub) {
         int64_t m = n - lo < sub ? n - lo : sub;
         for (int i = 0; i < sp.ncols; i++) {

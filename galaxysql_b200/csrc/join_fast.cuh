@@ -340,6 +340,35 @@ __device__ __forceinline__ unsigned long long pick(const unsigned long long (&w)
     return v;
 }
 
+
+// Writes the emitted rows of one thread: column loop outside (descriptor decoded once per column), row loop inside and
+// unrolled.  Consecutive lanes hold consecutive output positions, so every store instruction is coalesced.
+template <int R, int PW, int BP>
+__device__ __forceinline__ void write_rows(const OutMap &O, const unsigned long long (&pw)[R][PW], const unsigned long long (&bp)[R][BP],
+                                           const bool (&found)[R], const bool (&em)[R], const unsigned long long (&pos)[R], int32_t *flags) {
+#pragma unroll 1
+    for (int q = 0; q < O.nout; q++) {
+        const bool probe_side = O.side[q] == 0;
+        const int word = O.word[q];
+        const int sh = O.half[q] == 1 ? 32 : 0;
+        const bool is32 = O.is32[q] != 0;
+        char *data = reinterpret_cast<char *>(O.data[q]);
+        uint8_t *nulls = O.nulls[q];
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (!em[k]) continue;
+            unsigned long long v = probe_side ? pick<PW>(pw[k], word) : (word == 0 ? pw[k][0] : pick<BP>(bp[k], word - 1));
+            v >>= sh;
+            const bool isnull = !probe_side && !found[k];
+            if (isnull) v = 0;
+            if (nulls) nulls[pos[k]] = isnull ? 1 : 0;
+            else if (isnull) flags[FL_NULLOUT] = 1;
+            if (is32) st_stream_4(data + pos[k] * 4, (int)(unsigned)v);
+            else st_stream_8(data + pos[k] * 8, (long long)v);
+        }
+    }
+}
+
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
                                                       const __grid_constant__ Layout L, int64_t n, const unsigned long long *__restrict__ table,
@@ -461,27 +490,197 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
     __syncthreads();
     // 4. write the output columns: consecutive lanes -> consecutive positions (coalesced, evict-first)
     const unsigned long long base = tile_base;
+    bool em[RPT];
+    unsigned long long pos[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
-        if (!((ballot[k] >> lane) & 1u)) continue;
-        unsigned long long pos = base + cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
-#pragma unroll 1
-        for (int q = 0; q < O.nout; q++) {
-            unsigned long long v;
-            bool isnull = false;
-            if (O.side[q] == 0) {
-                v = pick<PW>(pw[k], O.word[q]);
-            } else {
-                isnull = !found[k];
-                v = O.word[q] == 0 ? pw[k][0] : pick<BP>(bp[k], O.word[q] - 1);
-            }
-            if (O.half[q] == 1) v >>= 32;
-            if (O.nulls[q]) O.nulls[q][pos] = isnull ? 1 : 0;
-            else if (isnull) flags[FL_NULLOUT] = 1;
-            if (isnull) v = 0;
-            if (O.is32[q]) st_stream_4(reinterpret_cast<int *>(O.data[q]) + pos, (int)(unsigned)v);
-            else st_stream_8(reinterpret_cast<long long *>(O.data[q]) + pos, (long long)v);
+        em[k] = (ballot[k] >> lane) & 1u;
+        pos[k] = base + cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+    }
+    write_rows<RPT, PW, BP>(O, pw, bp, found, em, pos, flags);
+}
+
+
+// ------------------------------------------------------------------------------------------------ TMA-staged probe
+// Persistent CTAs; a 4-stage shared-memory ring of packed probe tiles is kept full by one elected thread issuing 1-D
+// bulk TMA copies (cp.async.bulk, mbarrier complete_tx), so ~48 KB of HBM reads per CTA are in flight at all times
+// without holding registers.  Consumers read their rows from shared memory, issue all table reads (L2) before any is
+// used, compact with warp ballots and bump the global output cursor once per tile.
+constexpr int PT_RPT = 4;
+constexpr int PT_TILE = THREADS * PT_RPT;  // 1024 rows
+constexpr int PT_STAGES = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, unsigned long long *bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                 : "memory");
+}
+
+static size_t probe_tma_smem_bytes(int PW) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64; }
+
+template <int PW, int BW>
+__global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
+                                                             const unsigned long long *__restrict__ table, uint64_t nslots,
+                                                             const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long *ring = reinterpret_cast<unsigned long long *>(smem_raw);
+    unsigned long long *bars = ring + (size_t)PT_STAGES * PT_TILE * PW;
+    __shared__ unsigned int cell[2][THREADS / 32][PT_RPT];
+    __shared__ unsigned long long tile_base[2];
+    constexpr int BP = BW > 1 ? BW - 1 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    uint64_t pol_stream = 0;
+
+    auto issue = [&](int64_t tile, int stage) {  // called by thread 0 only
+        int64_t r0 = tile * PT_TILE;
+        int64_t rows = n - r0 < PT_TILE ? n - r0 : PT_TILE;
+        uint32_t bytes = (uint32_t)(((size_t)rows * PW * 8 + 15) & ~(size_t)15);  // the buffer has 16 B of slack
+        mbar_expect_tx(&bars[stage], bytes);
+        tma_load_1d(ring + (size_t)stage * PT_TILE * PW, packed + (size_t)r0 * PW, bytes, &bars[stage], pol_stream);
+    };
+    if (threadIdx.x == 0) {
+        pol_stream = l2_policy_evict_first();
+        for (int s = 0; s < PT_STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int s = 0; s < PT_STAGES; s++) {
+            int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+            if (t < ntiles) issue(t, s);
         }
+
+    for (int64_t i = 0;; i++) {
+        const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
+        if (tile >= ntiles) break;
+        const int stage = (int)(i % PT_STAGES);
+        const uint32_t parity = (uint32_t)((i / PT_STAGES) & 1);
+        const int db = (int)(i & 1);
+        const int64_t t0 = tile * PT_TILE;
+        mbar_wait(&bars[stage], parity);
+
+        unsigned long long pw[PT_RPT][PW];
+        unsigned long long bp[PT_RPT][BP];
+        unsigned long long tkey[PT_RPT];
+        uint64_t slot[PT_RPT];
+        bool found[PT_RPT], em[PT_RPT];
+        unsigned int ballot[PT_RPT];
+        const unsigned long long *src = ring + (size_t)stage * PT_TILE * PW;
+#pragma unroll
+        for (int k = 0; k < PT_RPT; k++) {
+            int idx = k * THREADS + threadIdx.x;
+            if (PW == 2) {
+                int4 v = *reinterpret_cast<const int4 *>(src + (size_t)idx * 2);
+                pw[k][0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                pw[k][PW - 1] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+            } else {
+#pragma unroll
+                for (int w = 0; w < PW; w++) pw[k][w] = src[(size_t)idx * PW + w];
+            }
+            if (t0 + idx >= n) pw[k][0] = KEY_EMPTY;
+            slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
+        }
+#pragma unroll
+        for (int k = 0; k < PT_RPT; k++) {  // all table reads in flight before any is consumed
+#pragma unroll
+            for (int w = 0; w < BP; w++) bp[k][w] = 0;
+            if (BW == 2) {
+                int4 v = ld_keep_16(table + slot[k] * 2, pol_keep);
+                tkey[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+            } else {
+                tkey[k] = ld_keep_8(table + slot[k] * BW, pol_keep);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PT_RPT; k++) {
+            const unsigned long long key = pw[k][0];
+            unsigned long long tk = tkey[k];
+            uint64_t s = slot[k];
+            found[k] = false;
+            if (key != KEY_EMPTY) {
+                while (tk != key && tk != KEY_EMPTY) {  // linear probing past other keys (rare at load <= 0.5)
+                    if (++s == nslots) s = 0;
+                    if (BW == 2) {
+                        int4 v = ld_keep_16(table + s * 2, pol_keep);
+                        tk = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                        bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+                    } else {
+                        tk = ld_keep_8(table + s * BW, pol_keep);
+                    }
+                }
+                if (tk == key) {
+                    found[k] = true;
+                    if (BW > 2) {
+#pragma unroll
+                        for (int w = 1; w < BW; w++) bp[k][w - 1] = ld_keep_8(table + s * BW + w, pol_keep);
+                    }
+                }
+            }
+            bool live = t0 + k * THREADS + threadIdx.x < n;
+            bool e;
+            switch (O.join_type) {
+            case GSQL_JOIN_INNER: e = found[k]; break;
+            case GSQL_JOIN_SEMI: e = found[k]; break;
+            case GSQL_JOIN_ANTI: e = !found[k]; break;
+            default: e = true; break;  // LEFT / RIGHT: unmatched probe rows are NULL-padded
+            }
+            em[k] = e && live;
+            ballot[k] = __ballot_sync(0xffffffffu, em[k]);
+            if (lane == 0) cell[db][warp][k] = __popc(ballot[k]);
+        }
+        __syncthreads();  // (A) every thread holds its rows in registers: the stage can be refilled; cells are complete
+        if (threadIdx.x == 0) {
+            int64_t nt = tile + (int64_t)PT_STAGES * gridDim.x;
+            if (nt < ntiles) issue(nt, stage);
+        }
+        if (warp == 0) {  // exclusive scan over the 32 (warp, k) cells + one cursor bump for the tile
+            unsigned int *flat = &cell[db][0][0];
+            unsigned int a = flat[lane], incl = a;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) tile_base[db] = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+            flat[lane] = incl - a;
+            static_assert((THREADS / 32) * PT_RPT == 32, "cell scan assumes 32 cells");
+        }
+        __syncthreads();  // (B)
+        const unsigned long long base = tile_base[db];
+        unsigned long long pos[PT_RPT];
+#pragma unroll
+        for (int k = 0; k < PT_RPT; k++) pos[k] = base + cell[db][warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+        write_rows<PT_RPT, PW, BP>(O, pw, bp, found, em, pos, flags);
     }
 }
 
