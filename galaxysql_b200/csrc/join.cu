@@ -542,7 +542,11 @@ static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::La
     {
         KernelScope ks(ctx, name.c_str());
         FJ_DISPATCH_W(W, {
-            GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static int attr_smem = 0;
+            if ((int)smem > attr_smem) {
+                GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                attr_smem = (int)smem;
+            }
             fj::k_fj_scatter<WW><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
         });
     }
@@ -864,7 +868,7 @@ static void fast_out_map(gsql_join *j, const ProbeParams &PP, fj::OutMap *O) {
 
 // Partition (when P > 1) + probe of `m` device-resident rows; output rows are appended at *cursor.
 static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m, unsigned long long *packed, const fj::OutMap &O,
-                                   unsigned long long *cursor) {
+                                   unsigned long long *cursor, unsigned long long *ticket) {
     JoinFast &F = j->fast;
     gsql_ctx *ctx = j->ctx;
     const int PW = F.pl.nwords, BW = F.bl.nwords;
@@ -874,6 +878,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         src = packed;
     }
     if (src && !env_i64("GSQL_JOIN_NO_TMA", 0)) {  // packed rows: TMA-staged persistent kernel
+        GSQL_CUDA(ctx, cudaMemsetAsync(ticket, 0, 8, ctx->stream));
         KernelScope ks(ctx, "join_fast_probe");
         size_t smem = fj::probe_tma_smem_bytes(PW);
         int64_t ntiles = div_up(m, fj::PT_TILE);
@@ -883,9 +888,13 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                              \
     if (PW == PWv && BW == BWv) {                                                                                                            \
-        GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        static bool attr_set = false;                                                                                                        \
+        if (!attr_set) {                                                                                                                     \
+            GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+            attr_set = true;                                                                                                                 \
+        }                                                                                                                                    \
         fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
-                                                                               F.flags.as<int32_t>());                                       \
+                                                                               ticket, F.flags.as<int32_t>());                               \
     }
         FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
         FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
@@ -1015,7 +1024,7 @@ static gsql_status fast_probe_host(gsql_join *j, const gsql_batch *probe, gsql_b
         }
         fj::OutMap O;
         fast_out_map(j, PP, &O);
-        if (st == GSQL_OK) st = fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, cursors.as<unsigned long long>() + i);
+        if (st == GSQL_OK) st = fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, cursors.as<unsigned long long>() + i, F.cursor.as<unsigned long long>() + 1);
         cudaMemcpyAsync(&hcount[i], cursors.as<unsigned long long>() + i, 8, cudaMemcpyDeviceToHost, ctx->stream);
         cudaEventRecord(comp_done[(size_t)i], ctx->stream);
         // C: D2H of slice i-1's output
@@ -1061,7 +1070,7 @@ static gsql_status fast_probe(gsql_join *j, const StagedBatch &sp, gsql_batch *o
             cols.c[i] = sp.cols[i];
             cols.c[i].data = (const char *)sp.cols[i].data + (size_t)lo * gsql_type_width(sp.cols[i].type);
         }
-        GSQL_TRY(fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, F.cursor.as<unsigned long long>()));
+        GSQL_TRY(fast_probe_rows(j, cols, m, packed.as<unsigned long long>(), O, F.cursor.as<unsigned long long>(), F.cursor.as<unsigned long long>() + 1));
     }
     unsigned long long total = 0;
     GSQL_CUDA(ctx, cudaMemcpyAsync(&total, F.cursor.p, 8, cudaMemcpyDeviceToHost, ctx->stream));

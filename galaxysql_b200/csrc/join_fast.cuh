@@ -341,30 +341,58 @@ __device__ __forceinline__ unsigned long long pick(const unsigned long long (&w)
 }
 
 
-// Writes the emitted rows of one thread: column loop outside (descriptor decoded once per column), row loop inside and
-// unrolled.  Consecutive lanes hold consecutive output positions, so every store instruction is coalesced.
+// Writes the emitted rows of one thread.  The column loop is outside; each column is dispatched ONCE (warp-uniform
+// switch) to a body whose source register (probe word J / build payload word J-PW) and extraction (low 32, high 32,
+// whole 64 bits) are compile-time, so a row-column costs an address computation and one store.  Consecutive lanes
+// hold consecutive output positions: every store instruction is coalesced.
+template <int R, int PW, int BP, int J, int H>
+__device__ __forceinline__ void write_col(char *data, uint8_t *nulls, bool null_if_unmatched, const unsigned long long (&pw)[R][PW],
+                                          const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                          const unsigned long long (&pos)[R], int32_t *flags) {
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        if (!em[k]) continue;
+        unsigned long long v = J < PW ? pw[k][J < PW ? J : 0] : bp[k][(J >= PW && J - PW < BP) ? J - PW : 0];
+        const bool isnull = null_if_unmatched && !found[k];
+        if (isnull) v = 0;
+        if (nulls) nulls[pos[k]] = isnull ? 1 : 0;
+        else if (isnull) flags[FL_NULLOUT] = 1;
+        if (H == 0) st_stream_4(data + pos[k] * 4, (int)(unsigned)v);
+        else if (H == 1) st_stream_4(data + pos[k] * 4, (int)(unsigned)(v >> 32));
+        else st_stream_8(data + pos[k] * 8, (long long)v);
+    }
+}
+
+template <int R, int PW, int BP, int J>
+__device__ __forceinline__ void write_col_h(int h, char *data, uint8_t *nulls, bool nu, const unsigned long long (&pw)[R][PW],
+                                            const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                            const unsigned long long (&pos)[R], int32_t *flags) {
+    if (h == 0) write_col<R, PW, BP, J, 0>(data, nulls, nu, pw, bp, found, em, pos, flags);
+    else if (h == 1) write_col<R, PW, BP, J, 1>(data, nulls, nu, pw, bp, found, em, pos, flags);
+    else write_col<R, PW, BP, J, 2>(data, nulls, nu, pw, bp, found, em, pos, flags);
+}
+
 template <int R, int PW, int BP>
 __device__ __forceinline__ void write_rows(const OutMap &O, const unsigned long long (&pw)[R][PW], const unsigned long long (&bp)[R][BP],
                                            const bool (&found)[R], const bool (&em)[R], const unsigned long long (&pos)[R], int32_t *flags) {
 #pragma unroll 1
     for (int q = 0; q < O.nout; q++) {
         const bool probe_side = O.side[q] == 0;
-        const int word = O.word[q];
-        const int sh = O.half[q] == 1 ? 32 : 0;
-        const bool is32 = O.is32[q] != 0;
+        // source register index: probe words 0..PW-1, then build payload words; the build key equals the probe key
+        const int j = probe_side ? O.word[q] : (O.word[q] == 0 ? 0 : PW + O.word[q] - 1);
+        // an INT32 column stored whole in a word (widened key) is its low half
+        const int h = O.is32[q] ? (O.half[q] == 1 ? 1 : 0) : 2;
         char *data = reinterpret_cast<char *>(O.data[q]);
         uint8_t *nulls = O.nulls[q];
-#pragma unroll
-        for (int k = 0; k < R; k++) {
-            if (!em[k]) continue;
-            unsigned long long v = probe_side ? pick<PW>(pw[k], word) : (word == 0 ? pw[k][0] : pick<BP>(bp[k], word - 1));
-            v >>= sh;
-            const bool isnull = !probe_side && !found[k];
-            if (isnull) v = 0;
-            if (nulls) nulls[pos[k]] = isnull ? 1 : 0;
-            else if (isnull) flags[FL_NULLOUT] = 1;
-            if (is32) st_stream_4(data + pos[k] * 4, (int)(unsigned)v);
-            else st_stream_8(data + pos[k] * 8, (long long)v);
+        const bool nu = !probe_side;
+        switch (j) {
+        case 0: write_col_h<R, PW, BP, 0>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        case 1: write_col_h<R, PW, BP, 1>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        case 2: write_col_h<R, PW, BP, 2>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        case 3: write_col_h<R, PW, BP, 3>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        case 4: write_col_h<R, PW, BP, 4>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        case 5: write_col_h<R, PW, BP, 5>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
+        default: write_col_h<R, PW, BP, 6>(h, data, nulls, nu, pw, bp, found, em, pos, flags); break;
         }
     }
 }
@@ -547,19 +575,26 @@ static size_t probe_tma_smem_bytes(int PW) { return (size_t)PT_STAGES * PT_TILE 
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
                                                              const unsigned long long *__restrict__ table, uint64_t nslots,
-                                                             const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
+                                                             const __grid_constant__ OutMap O, unsigned long long *cursor,
+                                                             unsigned long long *ticket, int32_t *flags) {
+    // `ticket` = tile ticket counter: tiles are handed out in index order so that all resident
+    // CTAs stay within a narrow window of tiles (one or two partitions -> the table slice stays in L2).
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *ring = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned long long *bars = ring + (size_t)PT_STAGES * PT_TILE * PW;
     __shared__ unsigned int cell[2][THREADS / 32][PT_RPT];
     __shared__ unsigned long long tile_base[2];
+    __shared__ long long stage_tile[PT_STAGES];
     constexpr int BP = BW > 1 ? BW - 1 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ntiles = (n + PT_TILE - 1) / PT_TILE;
     const uint64_t pol_keep = l2_policy_evict_last();
     uint64_t pol_stream = 0;
 
-    auto issue = [&](int64_t tile, int stage) {  // called by thread 0 only
+    auto issue = [&](int stage) {  // called by thread 0 only: take the next tile ticket and start its bulk copy
+        int64_t tile = (int64_t)atomicAdd(ticket, 1ULL);
+        stage_tile[stage] = tile < ntiles ? tile : -1;
+        if (tile >= ntiles) return;
         int64_t r0 = tile * PT_TILE;
         int64_t rows = n - r0 < PT_TILE ? n - r0 : PT_TILE;
         uint32_t bytes = (uint32_t)(((size_t)rows * PW * 8 + 15) & ~(size_t)15);  // the buffer has 16 B of slack
@@ -573,15 +608,13 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
     }
     __syncthreads();
     if (threadIdx.x == 0)
-        for (int s = 0; s < PT_STAGES; s++) {
-            int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
-            if (t < ntiles) issue(t, s);
-        }
+        for (int s = 0; s < PT_STAGES; s++) issue(s);
+    __syncthreads();
 
     for (int64_t i = 0;; i++) {
-        const int64_t tile = (int64_t)blockIdx.x + i * gridDim.x;
-        if (tile >= ntiles) break;
         const int stage = (int)(i % PT_STAGES);
+        const int64_t tile = stage_tile[stage];
+        if (tile < 0) break;  // tickets are monotonic: the first exhausted stage ends this CTA
         const uint32_t parity = (uint32_t)((i / PT_STAGES) & 1);
         const int db = (int)(i & 1);
         const int64_t t0 = tile * PT_TILE;
@@ -658,10 +691,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
             if (lane == 0) cell[db][warp][k] = __popc(ballot[k]);
         }
         __syncthreads();  // (A) every thread holds its rows in registers: the stage can be refilled; cells are complete
-        if (threadIdx.x == 0) {
-            int64_t nt = tile + (int64_t)PT_STAGES * gridDim.x;
-            if (nt < ntiles) issue(nt, stage);
-        }
+        if (threadIdx.x == 0) issue(stage);
         if (warp == 0) {  // exclusive scan over the 32 (warp, k) cells + one cursor bump for the tile
             unsigned int *flat = &cell[db][0][0];
             unsigned int a = flat[lane], incl = a;
