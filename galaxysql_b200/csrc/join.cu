@@ -864,6 +864,19 @@ static void fast_out_map(gsql_join *j, const ProbeParams &PP, fj::OutMap *O) {
         O->half[q] = (int8_t)L.half[j->out_col[q]];
         O->is32[q] = (int8_t)(j->out_types[q] == GSQL_T_INT32);
     }
+    int off = 0;  // shared-memory staging layout of one PT_TILE-row output tile: 8-byte columns first (alignment)
+    for (int pass = 0; pass < 2; pass++)
+        for (int q = 0; q < j->nout; q++) {
+            bool is32 = j->out_types[q] == GSQL_T_INT32;
+            if ((pass == 0) == is32) continue;
+            O->stage_off[q] = off;
+            off += fj::PT_TILE * (is32 ? 4 : 8);
+        }
+    for (int q = 0; q < j->nout; q++) {
+        O->stage_null_off[q] = off;
+        if (PP.out[q].nulls) off += fj::PT_TILE;
+    }
+    O->stage_bytes = off;
 }
 
 // Partition (when P > 1) + probe of `m` device-resident rows; output rows are appended at *cursor.
@@ -880,7 +893,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
     if (src && !env_i64("GSQL_JOIN_NO_TMA", 0)) {  // packed rows: TMA-staged persistent kernel
         GSQL_CUDA(ctx, cudaMemsetAsync(ticket, 0, 8, ctx->stream));
         KernelScope ks(ctx, "join_fast_probe");
-        size_t smem = fj::probe_tma_smem_bytes(PW);
+        size_t smem = fj::probe_tma_smem_bytes(PW, O.stage_bytes);
         int64_t ntiles = div_up(m, fj::PT_TILE);
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 3) per_sm = 3;
@@ -888,10 +901,10 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                              \
     if (PW == PWv && BW == BWv) {                                                                                                            \
-        static bool attr_set = false;                                                                                                        \
-        if (!attr_set) {                                                                                                                     \
+        static int attr_smem = 0;                                                                                                            \
+        if ((int)smem > attr_smem) {                                                                                                         \
             GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-            attr_set = true;                                                                                                                 \
+            attr_smem = (int)smem;                                                                                                           \
         }                                                                                                                                    \
         fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
                                                                                ticket, F.flags.as<int32_t>());                               \

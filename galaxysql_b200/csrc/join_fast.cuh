@@ -329,6 +329,9 @@ struct OutMap {
     int8_t is32[GSQL_MAX_COLS * 2];
     int32_t nout;
     int32_t join_type;
+    int32_t stage_off[GSQL_MAX_COLS * 2];   // byte offset of column q inside a tile's shared-memory output staging
+    int32_t stage_null_off[GSQL_MAX_COLS * 2];
+    int32_t stage_bytes;                    // staging bytes per tile (PT_TILE rows)
 };
 
 template <int W>
@@ -360,6 +363,84 @@ __device__ __forceinline__ void write_col(char *data, uint8_t *nulls, bool null_
         if (H == 0) st_stream_4(data + pos[k] * 4, (int)(unsigned)v);
         else if (H == 1) st_stream_4(data + pos[k] * 4, (int)(unsigned)(v >> 32));
         else st_stream_8(data + pos[k] * 8, (long long)v);
+    }
+}
+
+// Same dispatch, but into the tile's shared-memory staging area at local row index li (dense, 0..tile_total).
+template <int R, int PW, int BP, int J, int H>
+__device__ __forceinline__ void stage_col(char *stage, uint8_t *snull, bool null_if_unmatched, const unsigned long long (&pw)[R][PW],
+                                          const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                          const unsigned int (&li)[R]) {
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        if (!em[k]) continue;
+        unsigned long long v = J < PW ? pw[k][J < PW ? J : 0] : bp[k][(J >= PW && J - PW < BP) ? J - PW : 0];
+        const bool isnull = null_if_unmatched && !found[k];
+        if (isnull) v = 0;
+        if (snull) snull[li[k]] = isnull ? 1 : 0;
+        if (H == 0) reinterpret_cast<unsigned int *>(stage)[li[k]] = (unsigned)v;
+        else if (H == 1) reinterpret_cast<unsigned int *>(stage)[li[k]] = (unsigned)(v >> 32);
+        else reinterpret_cast<unsigned long long *>(stage)[li[k]] = v;
+    }
+}
+template <int R, int PW, int BP, int J>
+__device__ __forceinline__ void stage_col_h(int h, char *stage, uint8_t *snull, bool nu, const unsigned long long (&pw)[R][PW],
+                                            const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                            const unsigned int (&li)[R]) {
+    if (h == 0) stage_col<R, PW, BP, J, 0>(stage, snull, nu, pw, bp, found, em, li);
+    else if (h == 1) stage_col<R, PW, BP, J, 1>(stage, snull, nu, pw, bp, found, em, li);
+    else stage_col<R, PW, BP, J, 2>(stage, snull, nu, pw, bp, found, em, li);
+}
+template <int R, int PW, int BP>
+__device__ __forceinline__ void stage_rows(const OutMap &O, char *staging, const unsigned long long (&pw)[R][PW],
+                                           const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                           const unsigned int (&li)[R]) {
+#pragma unroll 1
+    for (int q = 0; q < O.nout; q++) {
+        const bool probe_side = O.side[q] == 0;
+        const int j = probe_side ? O.word[q] : (O.word[q] == 0 ? 0 : PW + O.word[q] - 1);
+        const int h = O.is32[q] ? (O.half[q] == 1 ? 1 : 0) : 2;
+        char *st = staging + O.stage_off[q];
+        uint8_t *sn = O.nulls[q] ? reinterpret_cast<uint8_t *>(staging + O.stage_null_off[q]) : nullptr;
+        const bool nu = !probe_side;
+        switch (j) {
+        case 0: stage_col_h<R, PW, BP, 0>(h, st, sn, nu, pw, bp, found, em, li); break;
+        case 1: stage_col_h<R, PW, BP, 1>(h, st, sn, nu, pw, bp, found, em, li); break;
+        case 2: stage_col_h<R, PW, BP, 2>(h, st, sn, nu, pw, bp, found, em, li); break;
+        case 3: stage_col_h<R, PW, BP, 3>(h, st, sn, nu, pw, bp, found, em, li); break;
+        case 4: stage_col_h<R, PW, BP, 4>(h, st, sn, nu, pw, bp, found, em, li); break;
+        case 5: stage_col_h<R, PW, BP, 5>(h, st, sn, nu, pw, bp, found, em, li); break;
+        default: stage_col_h<R, PW, BP, 6>(h, st, sn, nu, pw, bp, found, em, li); break;
+        }
+    }
+}
+
+// Cooperative write-out of a tile's staged columns: every warp store covers one ALIGNED 128-byte line of the output
+// column (partial sectors only at the two ends of the tile's range) — unaligned warp stores run at about half the
+// HBM write rate on B200 (tools/membench.cu).
+__device__ __forceinline__ void flush_staged(const OutMap &O, const char *staging, unsigned long long base, unsigned int cnt, int32_t *flags) {
+#pragma unroll 1
+    for (int q = 0; q < O.nout; q++) {
+        const char *st = staging + O.stage_off[q];
+        if (O.is32[q]) {
+            int *dst = reinterpret_cast<int *>(O.data[q]);
+            unsigned long long e0 = base & ~31ULL;
+            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
+                if (g >= base) st_stream_4(dst + g, reinterpret_cast<const int *>(st)[g - base]);
+        } else {
+            long long *dst = reinterpret_cast<long long *>(O.data[q]);
+            unsigned long long e0 = base & ~15ULL;
+            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
+                if (g >= base) st_stream_8(dst + g, reinterpret_cast<const long long *>(st)[g - base]);
+        }
+        if (O.nulls[q]) {
+            const uint8_t *sn = reinterpret_cast<const uint8_t *>(staging + O.stage_null_off[q]);
+            unsigned long long e0 = base & ~31ULL;
+            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
+                if (g >= base) O.nulls[q][g] = sn[g - base];
+        } else if (O.side[q] != 0 && O.join_type != GSQL_JOIN_INNER && O.join_type != GSQL_JOIN_SEMI && O.join_type != GSQL_JOIN_ANTI) {
+            if (threadIdx.x == 0) flags[FL_NULLOUT] = 1;  // outer join without a nulls buffer (rejected on the host)
+        }
     }
 }
 
@@ -570,7 +651,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  : "memory");
 }
 
-static size_t probe_tma_smem_bytes(int PW) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64; }
+static size_t probe_tma_smem_bytes(int PW, int stage_bytes) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64 + (size_t)stage_bytes; }
 
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
@@ -582,8 +663,10 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long *ring = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned long long *bars = ring + (size_t)PT_STAGES * PT_TILE * PW;
+    char *staging = reinterpret_cast<char *>(bars + 8);
     __shared__ unsigned int cell[2][THREADS / 32][PT_RPT];
     __shared__ unsigned long long tile_base[2];
+    __shared__ unsigned int tile_total[2];
     __shared__ long long stage_tile[PT_STAGES];
     constexpr int BP = BW > 1 ? BW - 1 : 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -701,16 +784,21 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
                 if (lane >= d) incl += t;
             }
             unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) tile_base[db] = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+            if (lane == 0) {
+                tile_base[db] = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+                tile_total[db] = total;
+            }
             flat[lane] = incl - a;
             static_assert((THREADS / 32) * PT_RPT == 32, "cell scan assumes 32 cells");
         }
         __syncthreads();  // (B)
-        const unsigned long long base = tile_base[db];
-        unsigned long long pos[PT_RPT];
+        unsigned int li[PT_RPT];
 #pragma unroll
-        for (int k = 0; k < PT_RPT; k++) pos[k] = base + cell[db][warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
-        write_rows<PT_RPT, PW, BP>(O, pw, bp, found, em, pos, flags);
+        for (int k = 0; k < PT_RPT; k++) li[k] = cell[db][warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+        stage_rows<PT_RPT, PW, BP>(O, staging, pw, bp, found, em, li);
+        __syncthreads();  // (C) the tile's output is dense in shared memory
+        flush_staged(O, staging, tile_base[db], tile_total[db], flags);
+        // no barrier needed here: the next staging writes come after the next iteration's (A) and (B)
     }
 }
 
