@@ -582,7 +582,7 @@ static gsql_status fast_build(gsql_join *j) {
     F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 256ll << 20);
     if (F.sub_batch < fj::TILE) F.sub_batch = fj::TILE;
     const int BW = F.bl.nwords;
-    int64_t want = j->build_rows * 2;
+    int64_t want = j->build_rows * env_i64("GSQL_JOIN_SLOTS_PER_ROW", 3);  // load factor 1/3: short probe sequences
     if (want < 1024) want = 1024;
     int64_t P = div_up(want * BW * 8, F.part_bytes);
     if (P > fj::MAX_P) P = fj::MAX_P;

@@ -285,36 +285,41 @@ __global__ void __launch_bounds__(THREADS) k_fj_insert(const unsigned long long 
         } else {
             pack_tile<W>(cols, L, t0 + threadIdx.x, n, w);
         }
-        // first attempt for all RPT rows at once (at load <= 0.5 most land in an empty slot), then the stragglers
-        uint64_t s[RPT];
+        // CAS attempts in rounds: every round issues one attempt for all still-unplaced rows of the thread
+        uint64_t sl[RPT];
         unsigned long long prev[RPT];
+        bool pending[RPT];
+        bool any = false;
 #pragma unroll
         for (int k = 0; k < RPT; k++) {
             int64_t r = t0 + k * THREADS + threadIdx.x;
-            s[k] = __umul64hi(key_hash(w[k][0]), nslots);
-            prev[k] = 1;  // "not attempted"
-            if (r < n) {
-                if (w[k][0] == KEY_EMPTY) flags[FL_SENTINEL] = 1;
-                else prev[k] = atomicCAS(table + s[k] * W, KEY_EMPTY, w[k][0]);
-            }
+            sl[k] = __umul64hi(key_hash(w[k][0]), nslots);
+            pending[k] = r < n;
+            if (pending[k] && w[k][0] == KEY_EMPTY) { flags[FL_SENTINEL] = 1; pending[k] = false; }
+            any |= pending[k];
         }
+        int disp = 0;
+        while (__any_sync(0xffffffffu, any)) {
 #pragma unroll
-        for (int k = 0; k < RPT; k++) {
-            int64_t r = t0 + k * THREADS + threadIdx.x;
-            if (r >= n || w[k][0] == KEY_EMPTY) continue;
-            unsigned long long p = prev[k];
-            uint64_t sl = s[k];
-            int disp = 0;
-            while (p != KEY_EMPTY) {
-                if (p == w[k][0]) { flags[FL_DUP] = 1; break; }  // duplicate build key: the generic (chained) path takes over
-                if (++sl == nslots) sl = 0;
-                if (++disp > MAX_DISP) { flags[FL_DISP] = 1; break; }
-                p = atomicCAS(table + sl * W, KEY_EMPTY, w[k][0]);
-            }
-            if (p == KEY_EMPTY) {
+            for (int k = 0; k < RPT; k++)
+                if (pending[k]) prev[k] = atomicCAS(table + sl[k] * W, KEY_EMPTY, w[k][0]);
+            any = false;
 #pragma unroll
-                for (int i = 1; i < W; i++) table[sl * W + i] = w[k][i];
+            for (int k = 0; k < RPT; k++) {
+                if (!pending[k]) continue;
+                if (prev[k] == KEY_EMPTY) {  // claimed: the payload words follow (visible after the kernel)
+#pragma unroll
+                    for (int i = 1; i < W; i++) table[sl[k] * W + i] = w[k][i];
+                    pending[k] = false;
+                } else if (prev[k] == w[k][0]) {  // duplicate build key: the generic (chained) path takes over
+                    flags[FL_DUP] = 1;
+                    pending[k] = false;
+                } else {
+                    if (++sl[k] == nslots) sl[k] = 0;
+                }
+                any |= pending[k];
             }
+            if (++disp > MAX_DISP) { if (any) flags[FL_DISP] = 1; break; }
         }
     }
 }
@@ -478,6 +483,69 @@ __device__ __forceinline__ void write_rows(const OutMap &O, const unsigned long 
     }
 }
 
+
+// Table lookups of the R rows a thread owns, organised in ROUNDS: every round issues the next slot read of all still
+// unresolved rows before any result is consumed, so a tile costs (longest probe sequence) dependent L2 round trips
+// instead of (sum over rows of the warp-wide longest sequence).  KEY_EMPTY rows (padding / the unbuildable key) never match.
+template <int R, int PW, int BW, int BP>
+__device__ __forceinline__ void lookup_rounds(const unsigned long long *__restrict__ table, uint64_t nslots, uint64_t pol,
+                                              const unsigned long long (&pw)[R][PW], unsigned long long (&bp)[R][BP], bool (&found)[R]) {
+    uint64_t slot[R];
+    unsigned long long tk[R];
+    bool pending[R];
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
+#pragma unroll
+        for (int i = 0; i < BP; i++) bp[k][i] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        if (BW == 2) {
+            int4 v = ld_keep_16(table + slot[k] * 2, pol);
+            tk[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+            bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+        } else {
+            tk[k] = ld_keep_8(table + slot[k] * BW, pol);
+        }
+    }
+    bool any = false;
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        pending[k] = pw[k][0] != KEY_EMPTY && tk[k] != pw[k][0] && tk[k] != KEY_EMPTY;
+        any |= pending[k];
+    }
+    while (__any_sync(0xffffffffu, any)) {  // linear probing past other keys, all unresolved rows advance together
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (pending[k]) {
+                if (++slot[k] == nslots) slot[k] = 0;
+                if (BW == 2) {
+                    int4 v = ld_keep_16(table + slot[k] * 2, pol);
+                    tk[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                    bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+                } else {
+                    tk[k] = ld_keep_8(table + slot[k] * BW, pol);
+                }
+            }
+        }
+        any = false;
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            pending[k] = pending[k] && tk[k] != pw[k][0] && tk[k] != KEY_EMPTY;
+            any |= pending[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) {
+        found[k] = pw[k][0] != KEY_EMPTY && tk[k] == pw[k][0];
+        if (BW > 2 && found[k]) {
+#pragma unroll
+            for (int i = 1; i < BW; i++) bp[k][i - 1] = ld_keep_8(table + slot[k] * BW + i, pol);
+        }
+    }
+}
+
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
                                                       const __grid_constant__ Layout L, int64_t n, const unsigned long long *__restrict__ table,
@@ -493,7 +561,6 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
     unsigned long long bp[RPT][BP];  // build payload words (the build key equals the probe key on a match)
     unsigned int ballot[RPT];
     bool found[RPT];
-    uint64_t slot[RPT];
 
     // 1. stream the probe rows in (all RPT loads in flight)
     if (packed) {
@@ -517,49 +584,11 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
     } else {
         pack_tile<PW>(cols, L, t0 + threadIdx.x, n, pw);
     }
-    // 2. one L2-resident table read per row, all RPT reads issued before any is consumed; then the rare walks.
-    //    A key equal to KEY_EMPTY (padding rows, and the one value the fast table never holds) cannot match.
-    unsigned long long tkey[RPT];
+    // 2. table lookups in rounds (one L2-resident read per row per round, all rows of the thread in flight)
 #pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        int64_t r = t0 + k * THREADS + threadIdx.x;
-        if (r >= n) pw[k][0] = KEY_EMPTY;
-        slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
-#pragma unroll
-        for (int i = 0; i < BP; i++) bp[k][i] = 0;
-        if (BW == 2) {
-            int4 v = ld_keep_16(table + slot[k] * 2, pol);
-            tkey[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
-            bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
-        } else {
-            tkey[k] = ld_keep_8(table + slot[k] * BW, pol);
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        unsigned long long key = pw[k][0];
-        unsigned long long tk = tkey[k];
-        uint64_t s = slot[k];
-        found[k] = false;
-        if (key == KEY_EMPTY) continue;
-        while (tk != key && tk != KEY_EMPTY) {  // linear probing past other keys
-            if (++s == nslots) s = 0;
-            if (BW == 2) {
-                int4 v = ld_keep_16(table + s * 2, pol);
-                tk = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
-                bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
-            } else {
-                tk = ld_keep_8(table + s * BW, pol);
-            }
-        }
-        if (tk == key) {
-            found[k] = true;
-            if (BW > 2) {
-#pragma unroll
-                for (int i = 1; i < BW; i++) bp[k][i - 1] = ld_keep_8(table + s * BW + i, pol);
-            }
-        }
-    }
+    for (int k = 0; k < RPT; k++)
+        if (t0 + k * THREADS + threadIdx.x >= n) pw[k][0] = KEY_EMPTY;
+    lookup_rounds<RPT, PW, BW, BP>(table, nslots, pol, pw, bp, found);
     // 3. which rows emit (AbstractBufferedJoinExec.nextRows:185-264 for unique build keys, no NULLs)
     unsigned int my_total = 0;
 #pragma unroll
@@ -705,8 +734,6 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
 
         unsigned long long pw[PT_RPT][PW];
         unsigned long long bp[PT_RPT][BP];
-        unsigned long long tkey[PT_RPT];
-        uint64_t slot[PT_RPT];
         bool found[PT_RPT], em[PT_RPT];
         unsigned int ballot[PT_RPT];
         const unsigned long long *src = ring + (size_t)stage * PT_TILE * PW;
@@ -722,45 +749,10 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
                 for (int w = 0; w < PW; w++) pw[k][w] = src[(size_t)idx * PW + w];
             }
             if (t0 + idx >= n) pw[k][0] = KEY_EMPTY;
-            slot[k] = __umul64hi(key_hash(pw[k][0]), nslots);
         }
-#pragma unroll
-        for (int k = 0; k < PT_RPT; k++) {  // all table reads in flight before any is consumed
-#pragma unroll
-            for (int w = 0; w < BP; w++) bp[k][w] = 0;
-            if (BW == 2) {
-                int4 v = ld_keep_16(table + slot[k] * 2, pol_keep);
-                tkey[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
-                bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
-            } else {
-                tkey[k] = ld_keep_8(table + slot[k] * BW, pol_keep);
-            }
-        }
+        lookup_rounds<PT_RPT, PW, BW, BP>(table, nslots, pol_keep, pw, bp, found);
 #pragma unroll
         for (int k = 0; k < PT_RPT; k++) {
-            const unsigned long long key = pw[k][0];
-            unsigned long long tk = tkey[k];
-            uint64_t s = slot[k];
-            found[k] = false;
-            if (key != KEY_EMPTY) {
-                while (tk != key && tk != KEY_EMPTY) {  // linear probing past other keys (rare at load <= 0.5)
-                    if (++s == nslots) s = 0;
-                    if (BW == 2) {
-                        int4 v = ld_keep_16(table + s * 2, pol_keep);
-                        tk = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
-                        bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
-                    } else {
-                        tk = ld_keep_8(table + s * BW, pol_keep);
-                    }
-                }
-                if (tk == key) {
-                    found[k] = true;
-                    if (BW > 2) {
-#pragma unroll
-                        for (int w = 1; w < BW; w++) bp[k][w - 1] = ld_keep_8(table + s * BW + w, pol_keep);
-                    }
-                }
-            }
             bool live = t0 + k * THREADS + threadIdx.x < n;
             bool e;
             switch (O.join_type) {
