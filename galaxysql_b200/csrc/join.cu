@@ -893,7 +893,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
     if (src && !env_i64("GSQL_JOIN_NO_TMA", 0)) {  // packed rows: TMA-staged persistent kernel
         GSQL_CUDA(ctx, cudaMemsetAsync(ticket, 0, 8, ctx->stream));
         KernelScope ks(ctx, "join_fast_probe");
-        size_t smem = fj::probe_tma_smem_bytes(PW, O.stage_bytes);
+        size_t smem = fj::probe_tma_smem_bytes(PW, BW);
         int64_t ntiles = div_up(m, fj::PT_TILE);
         int per_sm = (int)(220 * 1024 / (smem + 1024));
         if (per_sm > 3) per_sm = 3;
@@ -917,10 +917,17 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
     } else {
         KernelScope ks(ctx, "join_fast_probe");
         int grid = (int)div_up(m, fj::TILE);
-#define FJ_PROBE_CASE(PWv, BWv)                                                                                                         \
-    if (PW == PWv && BW == BWv)                                                                                                         \
-        fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, 0, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
-                                                                       cursor, F.flags.as<int32_t>());
+        size_t smem = fj::stage_words_bytes(PW, BW, fj::TILE);
+#define FJ_PROBE_CASE(PWv, BWv)                                                                                                            \
+    if (PW == PWv && BW == BWv) {                                                                                                          \
+        static int attr_smem = 0;                                                                                                          \
+        if ((int)smem > attr_smem) {                                                                                                       \
+            GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+            attr_smem = (int)smem;                                                                                                         \
+        }                                                                                                                                  \
+        fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
+                                                                          cursor, F.flags.as<int32_t>());                                  \
+    }
         FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
         FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
         FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
@@ -937,6 +944,9 @@ static bool fast_probe_applicable(gsql_join *j, const gsql_batch *probe, const g
     if (out_capacity < probe->rows) return false;  // <= 1 output row per probe row; smaller buffers take the exact two-pass path
     for (int i = 0; i < probe->ncols; i++)
         if (probe->cols[i].nulls) return false;
+    if (out->mem == GSQL_MEM_DEVICE)  // the flush uses 16-byte stores: caller buffers must be 16-byte aligned
+        for (int q = 0; q < j->nout; q++)
+            if (((uintptr_t)out->cols[q].data & 15) != 0) return false;
     if (j->outer_join)
         for (int q = 0; q < j->nout; q++)
             if (j->out_side[q] == SIDE_BUILD && !out->cols[q].nulls) {

@@ -371,82 +371,95 @@ __device__ __forceinline__ void write_col(char *data, uint8_t *nulls, bool null_
     }
 }
 
-// Same dispatch, but into the tile's shared-memory staging area at local row index li (dense, 0..tile_total).
-template <int R, int PW, int BP, int J, int H>
-__device__ __forceinline__ void stage_col(char *stage, uint8_t *snull, bool null_if_unmatched, const unsigned long long (&pw)[R][PW],
-                                          const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
-                                          const unsigned int (&li)[R]) {
+// ---- word-wise output staging ---------------------------------------------------------------------------------
+// A tile's emitted rows are compacted into shared memory as 8-byte WORD arrays (probe words, then build payload
+// words): sw[j][li].  The flush then produces each output column with 16-byte stores that are 16-byte aligned in the
+// OUTPUT (groups of 4 INT32 / 2 INT64-or-FP64 elements): ~2 instructions per row-column and full-sector writes
+// (unaligned warp stores reach only ~half the HBM write rate on B200 — tools/membench.cu).
+template <int R, int PW, int BP>
+__device__ __forceinline__ void stage_words(char *staging, int tile_rows, bool want_flags, const unsigned long long (&pw)[R][PW],
+                                            const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
+                                            const unsigned int (&li)[R]) {
+    unsigned long long *sw = reinterpret_cast<unsigned long long *>(staging);
+    uint8_t *sf = reinterpret_cast<uint8_t *>(staging) + (size_t)(PW + BP) * tile_rows * 8;
 #pragma unroll
     for (int k = 0; k < R; k++) {
         if (!em[k]) continue;
-        unsigned long long v = J < PW ? pw[k][J < PW ? J : 0] : bp[k][(J >= PW && J - PW < BP) ? J - PW : 0];
-        const bool isnull = null_if_unmatched && !found[k];
-        if (isnull) v = 0;
-        if (snull) snull[li[k]] = isnull ? 1 : 0;
-        if (H == 0) reinterpret_cast<unsigned int *>(stage)[li[k]] = (unsigned)v;
-        else if (H == 1) reinterpret_cast<unsigned int *>(stage)[li[k]] = (unsigned)(v >> 32);
-        else reinterpret_cast<unsigned long long *>(stage)[li[k]] = v;
+#pragma unroll
+        for (int j = 0; j < PW; j++) sw[(size_t)j * tile_rows + li[k]] = pw[k][j];
+#pragma unroll
+        for (int j = 0; j < BP; j++) sw[(size_t)(PW + j) * tile_rows + li[k]] = found[k] ? bp[k][j] : 0ULL;
+        if (want_flags) sf[li[k]] = found[k] ? 0 : 1;  // 1 = build side is NULL for this row
     }
 }
-template <int R, int PW, int BP, int J>
-__device__ __forceinline__ void stage_col_h(int h, char *stage, uint8_t *snull, bool nu, const unsigned long long (&pw)[R][PW],
-                                            const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
-                                            const unsigned int (&li)[R]) {
-    if (h == 0) stage_col<R, PW, BP, J, 0>(stage, snull, nu, pw, bp, found, em, li);
-    else if (h == 1) stage_col<R, PW, BP, J, 1>(stage, snull, nu, pw, bp, found, em, li);
-    else stage_col<R, PW, BP, J, 2>(stage, snull, nu, pw, bp, found, em, li);
-}
-template <int R, int PW, int BP>
-__device__ __forceinline__ void stage_rows(const OutMap &O, char *staging, const unsigned long long (&pw)[R][PW],
-                                           const unsigned long long (&bp)[R][BP], const bool (&found)[R], const bool (&em)[R],
-                                           const unsigned int (&li)[R]) {
+
+template <int PW, int BP>
+__device__ __forceinline__ void flush_words(const OutMap &O, const char *staging, int tile_rows, unsigned long long base, unsigned int cnt,
+                                            int32_t *flags) {
+    const unsigned long long end = base + cnt;
+    const uint8_t *sf = reinterpret_cast<const uint8_t *>(staging) + (size_t)(PW + BP) * tile_rows * 8;
 #pragma unroll 1
     for (int q = 0; q < O.nout; q++) {
         const bool probe_side = O.side[q] == 0;
         const int j = probe_side ? O.word[q] : (O.word[q] == 0 ? 0 : PW + O.word[q] - 1);
-        const int h = O.is32[q] ? (O.half[q] == 1 ? 1 : 0) : 2;
-        char *st = staging + O.stage_off[q];
-        uint8_t *sn = O.nulls[q] ? reinterpret_cast<uint8_t *>(staging + O.stage_null_off[q]) : nullptr;
-        const bool nu = !probe_side;
-        switch (j) {
-        case 0: stage_col_h<R, PW, BP, 0>(h, st, sn, nu, pw, bp, found, em, li); break;
-        case 1: stage_col_h<R, PW, BP, 1>(h, st, sn, nu, pw, bp, found, em, li); break;
-        case 2: stage_col_h<R, PW, BP, 2>(h, st, sn, nu, pw, bp, found, em, li); break;
-        case 3: stage_col_h<R, PW, BP, 3>(h, st, sn, nu, pw, bp, found, em, li); break;
-        case 4: stage_col_h<R, PW, BP, 4>(h, st, sn, nu, pw, bp, found, em, li); break;
-        case 5: stage_col_h<R, PW, BP, 5>(h, st, sn, nu, pw, bp, found, em, li); break;
-        default: stage_col_h<R, PW, BP, 6>(h, st, sn, nu, pw, bp, found, em, li); break;
+        const char *src = staging + (size_t)j * tile_rows * 8;
+        if (O.is32[q]) {
+            const unsigned int *s32 = reinterpret_cast<const unsigned int *>(src) + (O.half[q] == 1 ? 1 : 0);  // element i at s32[2*i]
+            int *dst = reinterpret_cast<int *>(O.data[q]);
+            const unsigned long long g0 = base & ~3ULL;
+            const unsigned int groups = (unsigned int)((end - g0 + 3) >> 2);
+            for (unsigned int grp = threadIdx.x; grp < groups; grp += THREADS) {
+                const unsigned long long g = g0 + 4ULL * grp;
+                if (g >= base && g + 4 <= end) {
+                    const unsigned int l = (unsigned int)(g - base);
+                    int4 v;
+                    v.x = (int)s32[2 * l];
+                    v.y = (int)s32[2 * l + 2];
+                    v.z = (int)s32[2 * l + 4];
+                    v.w = (int)s32[2 * l + 6];
+                    st_stream_16(dst + g, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        if (g + i >= base && g + i < end) st_stream_4(dst + g + i, (int)s32[2 * (unsigned int)(g + i - base)]);
+                }
+            }
+        } else {
+            const unsigned long long *s64 = reinterpret_cast<const unsigned long long *>(src);
+            long long *dst = reinterpret_cast<long long *>(O.data[q]);
+            const unsigned long long g0 = base & ~1ULL;
+            const unsigned int groups = (unsigned int)((end - g0 + 1) >> 1);
+            for (unsigned int grp = threadIdx.x; grp < groups; grp += THREADS) {
+                const unsigned long long g = g0 + 2ULL * grp;
+                if (g >= base && g + 2 <= end) {
+                    const unsigned int l = (unsigned int)(g - base);
+                    unsigned long long a = s64[l], b = s64[l + 1];
+                    int4 v;
+                    v.x = (int)(unsigned)a;
+                    v.y = (int)(unsigned)(a >> 32);
+                    v.z = (int)(unsigned)b;
+                    v.w = (int)(unsigned)(b >> 32);
+                    st_stream_16(dst + g, v);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 2; i++)
+                        if (g + i >= base && g + i < end) st_stream_8(dst + g + i, (long long)s64[(unsigned int)(g + i - base)]);
+                }
+            }
+        }
+        if (O.nulls[q]) {  // NULL flags: only build-side columns of an outer join can be NULL here
+            const bool outer = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
+            for (unsigned long long g = base + threadIdx.x; g < end; g += THREADS)
+                O.nulls[q][g] = (!probe_side && outer) ? sf[(unsigned int)(g - base)] : 0;
+        } else if (!probe_side && (O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT)) {
+            if (threadIdx.x == 0) flags[FL_NULLOUT] = 1;  // rejected on the host before launch
         }
     }
 }
 
-// Cooperative write-out of a tile's staged columns: every warp store covers one ALIGNED 128-byte line of the output
-// column (partial sectors only at the two ends of the tile's range) — unaligned warp stores run at about half the
-// HBM write rate on B200 (tools/membench.cu).
-__device__ __forceinline__ void flush_staged(const OutMap &O, const char *staging, unsigned long long base, unsigned int cnt, int32_t *flags) {
-#pragma unroll 1
-    for (int q = 0; q < O.nout; q++) {
-        const char *st = staging + O.stage_off[q];
-        if (O.is32[q]) {
-            int *dst = reinterpret_cast<int *>(O.data[q]);
-            unsigned long long e0 = base & ~31ULL;
-            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
-                if (g >= base) st_stream_4(dst + g, reinterpret_cast<const int *>(st)[g - base]);
-        } else {
-            long long *dst = reinterpret_cast<long long *>(O.data[q]);
-            unsigned long long e0 = base & ~15ULL;
-            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
-                if (g >= base) st_stream_8(dst + g, reinterpret_cast<const long long *>(st)[g - base]);
-        }
-        if (O.nulls[q]) {
-            const uint8_t *sn = reinterpret_cast<const uint8_t *>(staging + O.stage_null_off[q]);
-            unsigned long long e0 = base & ~31ULL;
-            for (unsigned long long g = e0 + threadIdx.x; g < base + cnt; g += THREADS)
-                if (g >= base) O.nulls[q][g] = sn[g - base];
-        } else if (O.side[q] != 0 && O.join_type != GSQL_JOIN_INNER && O.join_type != GSQL_JOIN_SEMI && O.join_type != GSQL_JOIN_ANTI) {
-            if (threadIdx.x == 0) flags[FL_NULLOUT] = 1;  // outer join without a nulls buffer (rejected on the host)
-        }
-    }
+static size_t stage_words_bytes(int PW, int BW, int tile_rows) {
+    int BP = BW > 1 ? BW - 1 : 1;
+    return (size_t)(PW + BP) * tile_rows * 8 + (size_t)tile_rows;
 }
 
 template <int R, int PW, int BP, int J>
@@ -552,6 +565,7 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
                                                       uint64_t nslots, const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
     __shared__ unsigned int cell[THREADS / 32][RPT];
     __shared__ unsigned long long tile_base;
+    __shared__ unsigned int tile_total;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t pol = l2_policy_evict_last();
     const int64_t t0 = (int64_t)blockIdx.x * TILE;
@@ -620,24 +634,29 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
         }
         unsigned int excl = incl - sum;
         unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 0) tile_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+        if (lane == 0) {
+            tile_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+            tile_total = total;
+        }
         flat[lane * 2] = excl;
         flat[lane * 2 + 1] = excl + a;
         static_assert(CELLS == 64, "cell scan assumes 64 cells");
     }
     __syncthreads();
-    // 4. write the output columns: consecutive lanes -> consecutive positions (coalesced, evict-first)
-    const unsigned long long base = tile_base;
+    // 4. compact the tile's rows into shared memory (word arrays), then flush the columns with aligned 16-byte stores
+    extern __shared__ __align__(16) unsigned char probe_stage[];
+    const bool want_flags = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
     bool em[RPT];
-    unsigned long long pos[RPT];
+    unsigned int li[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
         em[k] = (ballot[k] >> lane) & 1u;
-        pos[k] = base + cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+        li[k] = cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
     }
-    write_rows<RPT, PW, BP>(O, pw, bp, found, em, pos, flags);
+    stage_words<RPT, PW, BP>(reinterpret_cast<char *>(probe_stage), TILE, want_flags, pw, bp, found, em, li);
+    __syncthreads();
+    flush_words<PW, BP>(O, reinterpret_cast<const char *>(probe_stage), TILE, tile_base, tile_total, flags);
 }
-
 
 // ------------------------------------------------------------------------------------------------ TMA-staged probe
 // Persistent CTAs; a 4-stage shared-memory ring of packed probe tiles is kept full by one elected thread issuing 1-D
@@ -646,7 +665,7 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
 // used, compact with warp ballots and bump the global output cursor once per tile.
 constexpr int PT_RPT = 4;
 constexpr int PT_TILE = THREADS * PT_RPT;  // 1024 rows
-constexpr int PT_STAGES = 4;
+constexpr int PT_STAGES = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -680,7 +699,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
                  : "memory");
 }
 
-static size_t probe_tma_smem_bytes(int PW, int stage_bytes) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64 + (size_t)stage_bytes; }
+static size_t probe_tma_smem_bytes(int PW, int BW) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64 + stage_words_bytes(PW, BW, PT_TILE); }
 
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
@@ -787,9 +806,9 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
         unsigned int li[PT_RPT];
 #pragma unroll
         for (int k = 0; k < PT_RPT; k++) li[k] = cell[db][warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
-        stage_rows<PT_RPT, PW, BP>(O, staging, pw, bp, found, em, li);
+        stage_words<PT_RPT, PW, BP>(staging, PT_TILE, O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT, pw, bp, found, em, li);
         __syncthreads();  // (C) the tile's output is dense in shared memory
-        flush_staged(O, staging, tile_base[db], tile_total[db], flags);
+        flush_words<PW, BP>(O, staging, PT_TILE, tile_base[db], tile_total[db], flags);
         // no barrier needed here: the next staging writes come after the next iteration's (A) and (B)
     }
 }
