@@ -501,7 +501,7 @@ static fj::PartGeom fj_geom(gsql_ctx *ctx, int64_t rows, int P, int W) {
     g.P = P;
     size_t smem = fj::scatter_smem_bytes(W, P) + 4096;
     int per_sm = (int)(200 * 1024 / smem);
-    if (per_sm > 6) per_sm = 6;
+    if (per_sm > 2) per_sm = 2;  // 512-thread CTAs, <= 64 registers: two per SM
     if (per_sm < 1) per_sm = 1;
     int64_t nblocks = (int64_t)ctx->sm_count * per_sm;
     int64_t tiles = div_up(rows, fj::TILE);
@@ -611,7 +611,8 @@ static gsql_status fast_build(gsql_join *j) {
     }
     {
         KernelScope ks(ctx, "join_fast_insert");
-        int grid = grid_rows(ctx, div_up(j->build_rows, fj::RPT), 256, 6);
+        int64_t itiles = div_up(j->build_rows, fj::TILE);
+        int grid = (int)(itiles < (int64_t)ctx->sm_count * 2 ? itiles : (int64_t)ctx->sm_count * 2);
         FJ_DISPATCH_W(BW, {
             fj::k_fj_insert<WW><<<grid, fj::THREADS, 0, ctx->stream>>>(src, build, F.bl, j->build_rows, F.table.as<unsigned long long>(), F.nslots,
                                                                        F.flags.as<int32_t>());
@@ -890,7 +891,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed, F.flags.as<int32_t>(), "probe"));
         src = packed;
     }
-    if (src && !env_i64("GSQL_JOIN_NO_TMA", 0)) {  // packed rows: TMA-staged persistent kernel
+    if (src && env_i64("GSQL_JOIN_TMA", 0)) {  // opt-in: TMA-staged persistent kernel (measured slower than the plain tile kernel in r01)
         GSQL_CUDA(ctx, cudaMemsetAsync(ticket, 0, 8, ctx->stream));
         KernelScope ks(ctx, "join_fast_probe");
         size_t smem = fj::probe_tma_smem_bytes(PW, BW);
@@ -906,7 +907,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
             GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
             attr_smem = (int)smem;                                                                                                           \
         }                                                                                                                                    \
-        fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
+        fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::PT_THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
                                                                                ticket, F.flags.as<int32_t>());                               \
     }
         FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)

@@ -27,8 +27,8 @@
 namespace fj {
 
 constexpr unsigned long long KEY_EMPTY = 0x8000000000000000ULL;
-constexpr int THREADS = 256;
-constexpr int RPT = 8;                 // rows per thread per tile
+constexpr int THREADS = 512;           // 16 warps per CTA: two CTAs per SM give 32 resident warps at ~60 registers
+constexpr int RPT = 4;                 // rows per thread per tile
 constexpr int TILE = THREADS * RPT;    // 2048 rows
 constexpr int MAX_WORDS = 4;           // packed row = key word + up to 3 payload words
 constexpr int MAX_P = 1024;
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(THREADS) k_fj_hist(DCol keycol, PartGeom g, in
 
 // ---- pass 2: pack rows and scatter them into partition order through a shared-memory staged tile
 template <int W>
-__global__ void __launch_bounds__(THREADS) k_fj_scatter(const __grid_constant__ DColSet cols, const __grid_constant__ Layout L, PartGeom g,
+__global__ void __launch_bounds__(THREADS, 2) k_fj_scatter(const __grid_constant__ DColSet cols, const __grid_constant__ Layout L, PartGeom g,
                                                         const int64_t *__restrict__ offs, unsigned long long *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem_raw);           // TILE * W
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(THREADS) k_fj_table_init(unsigned long long *t
 // Inserts rows (packed, or packed on the fly from columns when `packed` == nullptr).  Tiles are taken in index order
 // so that concurrently running blocks work on neighbouring partitions (the table slice stays in L2).
 template <int W>
-__global__ void __launch_bounds__(THREADS) k_fj_insert(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
+__global__ void __launch_bounds__(THREADS, 2) k_fj_insert(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
                                                        const __grid_constant__ Layout L, int64_t n, unsigned long long *table, uint64_t nslots,
                                                        int32_t *flags) {
     for (int64_t t0 = (int64_t)blockIdx.x * TILE; t0 < n; t0 += (int64_t)gridDim.x * TILE) {
@@ -408,7 +408,7 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
             int *dst = reinterpret_cast<int *>(O.data[q]);
             const unsigned long long g0 = base & ~3ULL;
             const unsigned int groups = (unsigned int)((end - g0 + 3) >> 2);
-            for (unsigned int grp = threadIdx.x; grp < groups; grp += THREADS) {
+            for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
                 const unsigned long long g = g0 + 4ULL * grp;
                 if (g >= base && g + 4 <= end) {
                     const unsigned int l = (unsigned int)(g - base);
@@ -429,7 +429,7 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
             long long *dst = reinterpret_cast<long long *>(O.data[q]);
             const unsigned long long g0 = base & ~1ULL;
             const unsigned int groups = (unsigned int)((end - g0 + 1) >> 1);
-            for (unsigned int grp = threadIdx.x; grp < groups; grp += THREADS) {
+            for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
                 const unsigned long long g = g0 + 2ULL * grp;
                 if (g >= base && g + 2 <= end) {
                     const unsigned int l = (unsigned int)(g - base);
@@ -449,7 +449,7 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
         }
         if (O.nulls[q]) {  // NULL flags: only build-side columns of an outer join can be NULL here
             const bool outer = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
-            for (unsigned long long g = base + threadIdx.x; g < end; g += THREADS)
+            for (unsigned long long g = base + threadIdx.x; g < end; g += blockDim.x)
                 O.nulls[q][g] = (!probe_side && outer) ? sf[(unsigned int)(g - base)] : 0;
         } else if (!probe_side && (O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT)) {
             if (threadIdx.x == 0) flags[FL_NULLOUT] = 1;  // rejected on the host before launch
@@ -560,7 +560,7 @@ __device__ __forceinline__ void lookup_rounds(const unsigned long long *__restri
 }
 
 template <int PW, int BW>
-__global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
+__global__ void __launch_bounds__(THREADS, 2) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
                                                       const __grid_constant__ Layout L, int64_t n, const unsigned long long *__restrict__ table,
                                                       uint64_t nslots, const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
     __shared__ unsigned int cell[THREADS / 32][RPT];
@@ -663,8 +663,9 @@ __global__ void __launch_bounds__(THREADS) k_fj_probe(const unsigned long long *
 // bulk TMA copies (cp.async.bulk, mbarrier complete_tx), so ~48 KB of HBM reads per CTA are in flight at all times
 // without holding registers.  Consumers read their rows from shared memory, issue all table reads (L2) before any is
 // used, compact with warp ballots and bump the global output cursor once per tile.
+constexpr int PT_THREADS = 256;
 constexpr int PT_RPT = 4;
-constexpr int PT_TILE = THREADS * PT_RPT;  // 1024 rows
+constexpr int PT_TILE = PT_THREADS * PT_RPT;  // 1024 rows
 constexpr int PT_STAGES = 3;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -702,7 +703,7 @@ __device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, ui
 static size_t probe_tma_smem_bytes(int PW, int BW) { return (size_t)PT_STAGES * PT_TILE * PW * 8 + 64 + stage_words_bytes(PW, BW, PT_TILE); }
 
 template <int PW, int BW>
-__global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
+__global__ void __launch_bounds__(PT_THREADS, 3) k_fj_probe_tma(const unsigned long long *__restrict__ packed, int64_t n,
                                                              const unsigned long long *__restrict__ table, uint64_t nslots,
                                                              const __grid_constant__ OutMap O, unsigned long long *cursor,
                                                              unsigned long long *ticket, int32_t *flags) {
@@ -712,7 +713,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
     unsigned long long *ring = reinterpret_cast<unsigned long long *>(smem_raw);
     unsigned long long *bars = ring + (size_t)PT_STAGES * PT_TILE * PW;
     char *staging = reinterpret_cast<char *>(bars + 8);
-    __shared__ unsigned int cell[2][THREADS / 32][PT_RPT];
+    __shared__ unsigned int cell[2][PT_THREADS / 32][PT_RPT];
     __shared__ unsigned long long tile_base[2];
     __shared__ unsigned int tile_total[2];
     __shared__ long long stage_tile[PT_STAGES];
@@ -758,7 +759,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
         const unsigned long long *src = ring + (size_t)stage * PT_TILE * PW;
 #pragma unroll
         for (int k = 0; k < PT_RPT; k++) {
-            int idx = k * THREADS + threadIdx.x;
+            int idx = k * PT_THREADS + threadIdx.x;
             if (PW == 2) {
                 int4 v = *reinterpret_cast<const int4 *>(src + (size_t)idx * 2);
                 pw[k][0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
@@ -772,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
         lookup_rounds<PT_RPT, PW, BW, BP>(table, nslots, pol_keep, pw, bp, found);
 #pragma unroll
         for (int k = 0; k < PT_RPT; k++) {
-            bool live = t0 + k * THREADS + threadIdx.x < n;
+            bool live = t0 + k * PT_THREADS + threadIdx.x < n;
             bool e;
             switch (O.join_type) {
             case GSQL_JOIN_INNER: e = found[k]; break;
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_fj_probe_tma(const unsigned long
                 tile_total[db] = total;
             }
             flat[lane] = incl - a;
-            static_assert((THREADS / 32) * PT_RPT == 32, "cell scan assumes 32 cells");
+            static_assert((PT_THREADS / 32) * PT_RPT == 32, "cell scan assumes 32 cells");
         }
         __syncthreads();  // (B)
         unsigned int li[PT_RPT];
