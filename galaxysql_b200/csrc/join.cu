@@ -577,9 +577,9 @@ static gsql_status fast_build(gsql_join *j) {
     if (!fj::make_layout(j->build_types, j->n_build, j->bkey_cols[0], &F.bl)) return GSQL_OK;
     if (!fj::make_layout(j->probe_types, j->n_probe, j->pkey_cols[0], &F.pl)) return GSQL_OK;
     F.eligible = true;
-    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 32ll << 20);
+    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 16ll << 20);
     if (F.part_bytes < 4096) F.part_bytes = 4096;
-    F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 256ll << 20);
+    F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 1ll << 30);
     if (F.sub_batch < fj::TILE) F.sub_batch = fj::TILE;
     const int BW = F.bl.nwords;
     int64_t want = j->build_rows * env_i64("GSQL_JOIN_SLOTS_PER_ROW", 3);  // load factor 1/3: short probe sequences

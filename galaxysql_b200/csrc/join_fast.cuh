@@ -74,7 +74,9 @@ static bool make_layout(const int32_t *types, int ncols, int key_col, Layout *L)
     return next <= MAX_WORDS;
 }
 
-__device__ __forceinline__ uint64_t key_hash(unsigned long long k) { return gsql_fmix64(k); }
+// Fibonacci (multiplicative) hashing: the well-mixed HIGH bits of key * phi64 are exactly what the mulhi range
+// reductions (slot = mulhi(h, nslots), partition = mulhi(h, P)) consume; one 64-bit multiply instead of fmix64's two.
+__device__ __forceinline__ uint64_t key_hash(unsigned long long k) { return (k ^ (k >> 32)) * 0x9E3779B97F4A7C15ULL; }
 
 template <int W>
 __device__ __forceinline__ void pack_row(const DColSet &cols, const Layout &L, int64_t r, unsigned long long (&w)[W]) {
@@ -98,10 +100,48 @@ __device__ __forceinline__ void pack_row(const DColSet &cols, const Layout &L, i
     }
 }
 
-// Packs the RPT rows a thread owns in a tile (rows base + k*THREADS).  Column loop outside, row loop inside and
-// unrolled: RPT independent coalesced loads are in flight per column instead of one dependent load at a time.
+// Packs the RPT rows a thread owns in a tile (rows base + k*THREADS).  With a compile-time column count NC every load
+// of the tile (NC x RPT coalesced loads) is issued before the first one is consumed; NC = 0 is the generic fallback
+// (column loop not unrolled: RPT loads in flight per column).
+template <int W, int NC>
+__device__ __forceinline__ void pack_tile_nc(const DColSet &cols, const Layout &L, int64_t base, int64_t limit, unsigned long long (&w)[RPT][W]) {
+    unsigned long long v[NC > 0 ? NC : 1][RPT];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const DCol &col = cols.c[c];
+        const bool is32 = col.type == GSQL_T_INT32;
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            int64_t r = base + k * THREADS;
+            v[c][k] = 0;
+            if (r < limit) {
+                if (is32) v[c][k] = (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
+                else v[c][k] = (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RPT; k++)
+#pragma unroll
+        for (int i = 0; i < W; i++) w[k][i] = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const bool sext = c == L.key_col && cols.c[c].type == GSQL_T_INT32;
+        const int wi = L.word[c];
+        const int sh = L.half[c] == 1 ? 32 : 0;
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            unsigned long long vv = sext ? (unsigned long long)(long long)(int)(unsigned)v[c][k] : v[c][k];
+            vv <<= sh;
+#pragma unroll
+            for (int i = 0; i < W; i++)
+                if (i == wi) w[k][i] |= vv;
+        }
+    }
+}
+
 template <int W>
-__device__ __forceinline__ void pack_tile(const DColSet &cols, const Layout &L, int64_t base, int64_t limit, unsigned long long (&w)[RPT][W]) {
+__device__ __forceinline__ void pack_tile_generic(const DColSet &cols, const Layout &L, int64_t base, int64_t limit, unsigned long long (&w)[RPT][W]) {
 #pragma unroll
     for (int k = 0; k < RPT; k++)
 #pragma unroll
@@ -133,6 +173,17 @@ __device__ __forceinline__ void pack_tile(const DColSet &cols, const Layout &L, 
             for (int i = 0; i < W; i++)
                 if (i == wi) w[k][i] |= vv;
         }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void pack_tile(const DColSet &cols, const Layout &L, int64_t base, int64_t limit, unsigned long long (&w)[RPT][W]) {
+    switch (L.ncols) {  // warp-uniform
+    case 1: pack_tile_nc<W, 1>(cols, L, base, limit, w); break;
+    case 2: pack_tile_nc<W, 2>(cols, L, base, limit, w); break;
+    case 3: pack_tile_nc<W, 3>(cols, L, base, limit, w); break;
+    case 4: pack_tile_nc<W, 4>(cols, L, base, limit, w); break;
+    default: pack_tile_generic<W>(cols, L, base, limit, w); break;
     }
 }
 
