@@ -577,7 +577,10 @@ static gsql_status fast_build(gsql_join *j) {
     if (!fj::make_layout(j->build_types, j->n_build, j->bkey_cols[0], &F.bl)) return GSQL_OK;
     if (!fj::make_layout(j->probe_types, j->n_probe, j->pkey_cols[0], &F.pl)) return GSQL_OK;
     F.eligible = true;
-    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 16ll << 20);
+    // Default: one partition (probe straight from the input columns).  The radix-partitioned L2-resident mode
+    // (GSQL_JOIN_PART_BYTES=16777216) has the higher ceiling but its scatter pass still costs more than it saves (r01:
+    // 38.9 ms vs 37.0 ms per C2 step — DESIGN.md §Kernels).
+    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 1ll << 40);
     if (F.part_bytes < 4096) F.part_bytes = 4096;
     F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 1ll << 30);
     if (F.sub_batch < fj::TILE) F.sub_batch = fj::TILE;
