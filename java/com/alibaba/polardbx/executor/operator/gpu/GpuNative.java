@@ -1,0 +1,76 @@
+/*
+ * JNI surface of libgsql_gpu.so (include/gsql_gpu.h).  NOT compiled in this repository: the build image has no JDK.
+ * Drop into polardbx-executor next to the operators it serves; jni/gsql_jni.c is the matching C shim.
+ */
+package com.alibaba.polardbx.executor.operator.gpu;
+
+public final class GpuNative {
+    static {
+        System.loadLibrary("gsql_jni"); // links libgsql_gpu.so
+    }
+
+    private GpuNative() {
+    }
+
+    public static final int T_INT32 = 0, T_INT64 = 1, T_FP64 = 2, T_DEC128 = 3;
+
+    /** gsql_ctx_create; one context per (driver thread group, device). Throws TddlRuntimeException when no GPU. */
+    public static native long ctxCreate(int device);
+
+    public static native void ctxDestroy(long ctx);
+
+    /**
+     * A staging batch: pinned host memory owned by the native side (gsql_host_alloc), filled from Block arrays with
+     * GetPrimitiveArrayCritical + memcpy.  columns[i] is int[] / long[] / double[] (IntegerBlock.intArray(),
+     * LongBlock.longArray(), DoubleBlock.doubleArray()); nulls[i] is boolean[] or null (AbstractBlock.nulls()).
+     */
+    public static native long stagingCreate(int[] types, int capacityRows);
+
+    public static native void stagingAppend(long staging, Object[] columns, boolean[][] nulls, int arrayOffset, int rows);
+
+    public static native int stagingRows(long staging);
+
+    public static native void stagingReset(long staging);
+
+    public static native void stagingDestroy(long staging);
+
+    // ---- hash join (gsql_join_*)
+    public static native long joinCreate(long ctx, int joinType, boolean maxOneRow, boolean buildOuter, int[] outerKeys,
+                                         int[] innerKeys, int[] keyTypes, int[] outerTypes, int[] innerTypes,
+                                         int[] antiOperands, int[] condCols, long[] condNeValues, long expectedBuildRows);
+
+    public static native void joinBuildConsume(long join, long staging);
+
+    public static native void joinBuildFinish(long join);
+
+    /** Probes the staged rows; results land in `outStaging` (grown as needed). Returns the output row count. */
+    public static native int joinProbe(long join, long probeStaging, long outStaging);
+
+    public static native int joinUnmatchedBuild(long join, long outStaging);
+
+    public static native void joinDestroy(long join);
+
+    // ---- hash aggregation (gsql_agg_*)
+    public static native long aggCreate(long ctx, int[] inputTypes, int[] groups, int[] aggKinds, int[][] aggCols,
+                                        int[] filterArgs, long expectedGroups);
+
+    public static native void aggConsume(long agg, long staging);
+
+    public static native long aggFinish(long agg);
+
+    public static native int aggNext(long agg, long outStaging, int maxRows);
+
+    public static native void aggDestroy(long agg);
+
+    // ---- local hash-partition exchange (gsql_xchg_partition)
+    public static native long xchgCreate(long ctx, int[] types, int[] channels, int[] keyTypes, int nparts);
+
+    public static native void xchgPartition(long xchg, long inStaging, long outStaging, long[] partCounts);
+
+    public static native void xchgDestroy(long xchg);
+
+    /** Copies rows [from, from+rows) of staged column `col` into a fresh Java array (int[] / long[] / double[]). */
+    public static native Object stagingColumn(long staging, int col, int from, int rows);
+
+    public static native boolean[] stagingNulls(long staging, int col, int from, int rows);
+}
