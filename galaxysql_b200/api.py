@@ -344,7 +344,10 @@ class HashAgg:
 
     def __init__(self, ctx: Context, input_types: Sequence[int], groups: Sequence[int],
                  aggs: Sequence[Tuple[int, Sequence[int]]], expected_groups: int = 1024,
-                 filter_args: Optional[Sequence[int]] = None):
+                 filter_args: Optional[Sequence[int]] = None,
+                 derived: Sequence[Tuple[int, int, int, int]] = (), row_filter: Optional[Tuple[int, int, int]] = None):
+        """derived: (kind, a, b, c) fused FP64 expressions addressed as columns len(input_types)+i;
+        row_filter: (column, gsql_cmp_op, value) fused scan-side predicate."""
         self.ctx = ctx
         s = N.AggSpec()
         s.n_input_cols = len(input_types)
@@ -361,6 +364,13 @@ class HashAgg:
                 s.aggs[i].cols[k] = c
             s.aggs[i].filter_arg = filter_args[i] if filter_args else -1
         s.expected_groups = expected_groups
+        s.n_derived = len(derived)
+        for i, (kind, a_, b_, c_) in enumerate(derived):
+            s.derived[i].kind, s.derived[i].a, s.derived[i].b, s.derived[i].c = kind, a_, b_, c_
+        if row_filter is not None:
+            s.row_filter_col, s.row_filter_op, s.row_filter_value = row_filter
+        else:
+            s.row_filter_col, s.row_filter_op = -1, N.CMP_NONE
         h = C.c_void_p()
         ctx.check(ctx.lib.gsql_agg_create(ctx.ptr, C.byref(s), C.byref(h)))
         self.h = h

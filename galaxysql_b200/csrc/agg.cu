@@ -13,6 +13,10 @@
 // (lo/hi with carry), which equals the reference's long-with-overflow-escape-to-DECIMAL result.
 // Two specialisations sit in front of the generic kernel (agg_fast.cuh): a shared-memory privatised table for
 // low-cardinality group-bys and a key-in-slot table for single-integer-key high-cardinality group-bys.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -50,6 +54,9 @@ struct AggParams {
     const int64_t *row_list;       // non-null: process these rows (overflow re-run) instead of [row0, row0+rows)
     int64_t row0, rows;
     int64_t gcap;                  // groups the arrays can hold before a grow (a slack margin sits above it)
+    int32_t n_derived, rf_col, rf_op, pad2;
+    int64_t rf_value;
+    gsql_derived_col derived[GSQL_MAX_DERIVED];
 };
 
 // canonical 8-byte image of a key component; NULL has its own flag
@@ -81,32 +88,37 @@ __host__ __device__ __forceinline__ double dbl_unsortable(long long s, bool for_
 
 __device__ __forceinline__ bool in_null(const DCol &c, int64_t r) { return c.nulls != nullptr && c.nulls[r] != 0; }
 
-// Finds or creates the group of input row r.  Returns gid >= 0, or -1 when the table is full (row -> overflow).
-__device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
+// Table digest of a canonical key image: the key itself for a single key column (exact), a 64-bit mix otherwise.
+__device__ __forceinline__ unsigned long long digest_of_keys(const AggParams &P, const int64_t (&kv)[GSQL_MAX_KEYS], const bool (&kn)[GSQL_MAX_KEYS]) {
+    if (P.exact) return (unsigned long long)kv[0];
+    unsigned long long h = 0x243F6A8885A308D3ULL;
+#pragma unroll 1
+    for (int c = 0; c < P.nkeys; c++)
+        h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (kn[c] ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+    if (h == DIGEST_EMPTY) h ^= 1;
+    return h;
+}
+
+// Canonical key image of input row r (values + NULL flags) and its table digest.
+__device__ __forceinline__ unsigned long long load_group_key(const AggParams &P, int64_t r, int64_t (&kv)[GSQL_MAX_KEYS], bool (&kn)[GSQL_MAX_KEYS]) {
+#pragma unroll 1
+    for (int c = 0; c < P.nkeys; c++) {
+        KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
+        kn[c] = k.is_null;
+        kv[c] = canon_key(k, P.keys.utype[c]);
+    }
+    return digest_of_keys(P, kv, kn);
+}
+
+// Finds or creates the group with key (kv, kn) / digest d.  Returns gid >= 0, or -1 when the table is full.
+__device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (&kv)[GSQL_MAX_KEYS], const bool (&kn)[GSQL_MAX_KEYS],
+                                             unsigned long long d, bool ignore_cap = false) {
     if (P.nkeys == 0) return 0;
-    int64_t kv[GSQL_MAX_KEYS];
-    bool kn[GSQL_MAX_KEYS];
-    unsigned long long d;
     uint64_t s;
     bool dedicated = false;
     if (P.exact) {
-        KeyVal k = gsql_load_key(P.keys.c[0], r, P.keys.utype[0]);
-        kn[0] = k.is_null;
-        kv[0] = canon_key(k, P.keys.utype[0]);
-        d = (unsigned long long)kv[0];
-        if (k.is_null) { s = P.nslots + 1; dedicated = true; }          // NULL group key is an ordinary key (Block.java:136-145)
+        if (kn[0]) { s = P.nslots + 1; dedicated = true; }          // NULL group key is an ordinary key (Block.java:136-145)
         else if (d == DIGEST_EMPTY) { s = P.nslots; dedicated = true; }
-    } else {
-        unsigned long long h = 0x243F6A8885A308D3ULL;
-#pragma unroll 1
-        for (int c = 0; c < P.nkeys; c++) {
-            KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
-            kn[c] = k.is_null;
-            kv[c] = canon_key(k, P.keys.utype[c]);
-            h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (k.is_null ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
-        }
-        if (h == DIGEST_EMPTY) h ^= 1;
-        d = h;
     }
     if (!dedicated) s = __umul64hi(gsql_fmix64(d), P.nslots);
     while (true) {
@@ -118,7 +130,7 @@ __device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
             unsigned long long prev = cur == DIGEST_EMPTY ? atomicCAS(&sl->digest, DIGEST_EMPTY, 1ULL) : cur;
             if (prev == DIGEST_EMPTY) mine = true;
         } else if (cur == DIGEST_EMPTY) {
-            if (*reinterpret_cast<volatile unsigned long long *>(&P.counters[C_NGROUPS]) >= (unsigned long long)P.gcap) return -1;
+            if (!ignore_cap && *reinterpret_cast<volatile unsigned long long *>(&P.counters[C_NGROUPS]) >= (unsigned long long)P.gcap) return -1;
             unsigned long long prev = atomicCAS(&sl->digest, DIGEST_EMPTY, d);
             if (prev == DIGEST_EMPTY) mine = true;
             else cur = prev;
@@ -150,6 +162,14 @@ __device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
     }
 }
 
+__device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
+    if (P.nkeys == 0) return 0;
+    int64_t kv[GSQL_MAX_KEYS];
+    bool kn[GSQL_MAX_KEYS];
+    unsigned long long d = load_group_key(P, r, kv, kn);
+    return find_group_kv(P, kv, kn, d);
+}
+
 __device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {
     if (c.type == GSQL_T_INT32) return reinterpret_cast<const int32_t *>(c.data)[r];
     if (c.type == GSQL_T_INT64) return reinterpret_cast<const int64_t *>(c.data)[r];
@@ -159,6 +179,42 @@ __device__ __forceinline__ double in_f64(const DCol &c, int64_t r) {
     if (c.type == GSQL_T_FP64) return reinterpret_cast<const double *>(c.data)[r];
     if (c.type == GSQL_T_INT64) return (double)reinterpret_cast<const int64_t *>(c.data)[r];
     return (double)reinterpret_cast<const int32_t *>(c.data)[r];
+}
+
+// Column `col` of row r as the aggregators see it: a plain input column, or a fused derived expression
+// (VectorizedProjectExec replacement): NULL when any operand is NULL.
+__device__ __forceinline__ bool val_null(const AggParams &P, int col, int64_t r) {
+    if (col < P.in.n) return in_null(P.in.c[col], r);
+    const gsql_derived_col &d = P.derived[col - P.in.n];
+    bool n = in_null(P.in.c[d.a], r) || in_null(P.in.c[d.b], r);
+    if (d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) n = n || in_null(P.in.c[d.c], r);
+    return n;
+}
+__device__ __forceinline__ double val_f64(const AggParams &P, int col, int64_t r) {
+    if (col < P.in.n) return in_f64(P.in.c[col], r);
+    const gsql_derived_col &d = P.derived[col - P.in.n];
+    double x = in_f64(P.in.c[d.a], r) * (1.0 - in_f64(P.in.c[d.b], r));
+    if (d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) x = x * (1.0 + in_f64(P.in.c[d.c], r));
+    return x;
+}
+__device__ __forceinline__ int64_t val_i64(const AggParams &P, int col, int64_t r) {
+    if (col < P.in.n) return in_i64(P.in.c[col], r);
+    return (int64_t)val_f64(P, col, r);
+}
+// fused scan-side predicate (VectorizedFilterExec replacement); NULL never passes
+__device__ __forceinline__ bool row_passes(const AggParams &P, int64_t r) {
+    if (P.rf_op == GSQL_CMP_NONE) return true;
+    const DCol &c = P.in.c[P.rf_col];
+    if (in_null(c, r)) return false;
+    int64_t v = in_i64(c, r);
+    switch (P.rf_op) {
+    case GSQL_CMP_LE: return v <= P.rf_value;
+    case GSQL_CMP_LT: return v < P.rf_value;
+    case GSQL_CMP_GE: return v >= P.rf_value;
+    case GSQL_CMP_GT: return v > P.rf_value;
+    case GSQL_CMP_EQ: return v == P.rf_value;
+    default: return v != P.rf_value;
+    }
 }
 
 __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, int gid, int64_t r) {
@@ -172,19 +228,19 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
         return;
     case GSQL_AGG_COUNT:
         for (int i = 0; i < a.ncols; i++)
-            if (in_null(P.in.c[a.cols[i]], r)) return;
+            if (val_null(P, a.cols[i], r)) return;
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
         return;
     default: break;
     }
-    const DCol &c = P.in.c[a.cols[0]];
-    if (in_null(c, r)) return;
+    const int c = a.cols[0];
+    if (val_null(P, c, r)) return;
     switch (a.kind) {
     case GSQL_AGG_SUM:
         if (a.in_type == GSQL_T_FP64) {
-            atomicAdd(&a.d[gid], in_f64(c, r));
+            atomicAdd(&a.d[gid], val_f64(P, c, r));
         } else {  // exact 128-bit: lo += v (carry out), hi += sign extension + carry
-            long long v = in_i64(c, r);
+            long long v = val_i64(P, c, r);
             unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)v);
             unsigned long long sum = old + (unsigned long long)v;
             long long carry = (sum < old ? 1 : 0) + (v < 0 ? -1 : 0);
@@ -193,17 +249,17 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
         a.has[gid] = 1;
         return;
     case GSQL_AGG_AVG:
-        atomicAdd(&a.d[gid], in_f64(c, r));
+        atomicAdd(&a.d[gid], val_f64(P, c, r));
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
         a.has[gid] = 1;
         return;
     case GSQL_AGG_SUM0:
-        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)in_i64(c, r));
+        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, c, r));
         return;
     case GSQL_AGG_MIN:
     case GSQL_AGG_MAX: {
         bool mx = a.kind == GSQL_AGG_MAX;
-        long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(in_f64(c, r), mx) : in_i64(c, r);
+        long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(val_f64(P, c, r), mx) : val_i64(P, c, r);
         if (mx) atomicMax(reinterpret_cast<long long *>(&a.l[gid]), v);
         else atomicMin(reinterpret_cast<long long *>(&a.l[gid]), v);
         a.has[gid] = 1;
@@ -216,6 +272,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
 __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ AggParams P) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.rows; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = P.row_list ? P.row_list[i] : P.row0 + i;
+        if (!row_passes(P, r)) continue;
         int gid = find_group(P, r);
         if (gid < 0) {
             unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
@@ -461,6 +518,11 @@ static void agg_fill_params(gsql_agg *a, const StagedBatch *sb, AggParams *P) {
     P->counters = a->counters.as<unsigned long long>();
     P->overflow_rows = a->overflow.as<int64_t>();
     P->gcap = a->gcap;
+    P->n_derived = a->spec.n_derived;
+    for (int i = 0; i < a->spec.n_derived; i++) P->derived[i] = a->spec.derived[i];
+    P->rf_col = a->spec.row_filter_col;
+    P->rf_op = a->spec.row_filter_op;
+    P->rf_value = a->spec.row_filter_value;
 }
 
 extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec, gsql_agg **out) {
@@ -475,6 +537,20 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
         if (s.input_types[i] < GSQL_T_INT32 || s.input_types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "input col %d type", i);
     for (int k = 0; k < s.ngroups; k++)
         if (s.groups[k] < 0 || s.groups[k] >= s.n_input_cols) return gsql_set_error(ctx, GSQL_E_INVALID, "group col out of range");
+    if (s.n_derived < 0 || s.n_derived > GSQL_MAX_DERIVED) return gsql_set_error(ctx, GSQL_E_INVALID, "bad derived column count");
+    for (int i = 0; i < s.n_derived; i++) {
+        const gsql_derived_col &d = s.derived[i];
+        if (d.kind != GSQL_EXPR_MUL_1MINUS && d.kind != GSQL_EXPR_MUL_1MINUS_1PLUS) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "derived column %d: expression kind", i);
+        int nops = d.kind == GSQL_EXPR_MUL_1MINUS ? 2 : 3;
+        const int ops[3] = {d.a, d.b, d.c};
+        for (int q = 0; q < nops; q++)
+            if (ops[q] < 0 || ops[q] >= s.n_input_cols) return gsql_set_error(ctx, GSQL_E_INVALID, "derived column %d: operand out of range", i);
+    }
+    if (s.row_filter_op != GSQL_CMP_NONE) {
+        if (s.row_filter_op < GSQL_CMP_LE || s.row_filter_op > GSQL_CMP_NE || s.row_filter_col < 0 || s.row_filter_col >= s.n_input_cols ||
+            s.input_types[s.row_filter_col] == GSQL_T_FP64)
+            return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "row filter must compare an INT/BIGINT input column");
+    }
     gsql_agg *a = new gsql_agg();
     a->ctx = ctx;
     a->spec = s;
@@ -487,16 +563,18 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
         int need = c.kind == GSQL_AGG_COUNT_STAR ? 0 : 1;
         if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != 1)) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
         for (int q = 0; q < c.ncols; q++)
-            if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
+            if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols + s.n_derived) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
         if (c.filter_arg >= s.n_input_cols) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: filter column", i); }
-        a->in_type[i] = c.ncols > 0 ? s.input_types[c.cols[0]] : GSQL_T_INT64;
+        a->in_type[i] = c.ncols > 0 ? (c.cols[0] < s.n_input_cols ? s.input_types[c.cols[0]] : GSQL_T_FP64) : GSQL_T_INT64;
         // planner-time fall-through cases (the stock HashAggExec keeps them): AVG over integers is DECIMAL division
         if (c.kind == GSQL_AGG_AVG && a->in_type[i] != GSQL_T_FP64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG(integer) -> DECIMAL not on the GPU path"); }
         if (c.kind == GSQL_AGG_SUM0 && a->in_type[i] != GSQL_T_INT64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "SUM0 needs BIGINT input"); }
         a->out_types[a->nout++] = agg_out_type(c.kind, a->in_type[i]);
     }
     cudaSetDevice(ctx->device);
-    a->slack = (int64_t)ctx->sm_count * 2048 + 1024;
+    agg_fast_plan(&a->fast, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
+    a->slack = (int64_t)ctx->sm_count * 2048 + 1024 + (int64_t)ctx->sm_count * 2 * 1024;  // + CTA-table merges of the smem path
     int64_t gcap = s.expected_groups > 0 ? s.expected_groups : 1024;
     if (gcap < 65536) gcap = 65536;
     gsql_status st = a->counters.alloc(ctx, C_COUNT * 8);
@@ -543,14 +621,27 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     P.rows = batch->rows;
     P.row_list = nullptr;
     DevBuf pending;  // overflow rows being re-run
+    bool first = true;
     while (true) {
-        {
+        if (first && a->fast.eligible && a->fast.enabled) {  // shared-memory privatised tables (low-cardinality shapes)
+            KernelScope ks(ctx, "agg_smem");
+            int64_t warps = div_up(P.rows, 32);
+            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, div_up(warps, AF_THREADS / 32));
+            if (grid < 1) grid = 1;
+            k_agg_smem<<<grid, AF_THREADS, a->fast.L.total, ctx->stream>>>(P, a->fast.L);
+        } else {
             KernelScope ks(ctx, "agg_consume");
             k_agg_consume<<<grid_rows(ctx, P.rows, 256, 8), 256, 0, ctx->stream>>>(P);
         }
         GSQL_CUDA(ctx, cudaGetLastError());
         unsigned long long h[C_COUNT];
         GSQL_TRY(agg_read_counters(a, h));
+        if (first && a->fast.eligible && a->fast.enabled) {  // adaptive: stop when the CTA tables do not hold the key set
+            a->fast.rows_seen += P.rows;
+            a->fast.rows_fallback = (int64_t)h[C_FALLBACK];
+            if (a->fast.rows_seen >= (1 << 16) && a->fast.rows_fallback * 8 > a->fast.rows_seen) a->fast.enabled = false;
+        }
+        first = false;
         a->ngroups = (int64_t)h[C_NGROUPS];
         int64_t nover = (int64_t)h[C_OVERFLOW];
         if (nover == 0) break;

@@ -71,12 +71,23 @@ class AggCall(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ncols", C.c_int32), ("cols", C.c_int32 * 4), ("filter_arg", C.c_int32)]
 
 
+class DerivedCol(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("c", C.c_int32)]
+
+
+MAX_DERIVED = 4
+EXPR_MUL_1MINUS, EXPR_MUL_1MINUS_1PLUS = 1, 2
+CMP_NONE, CMP_LE, CMP_LT, CMP_GE, CMP_GT, CMP_EQ, CMP_NE = range(7)
+
+
 class AggSpec(C.Structure):
     _fields_ = [
         ("n_input_cols", C.c_int32), ("input_types", C.c_int32 * MAX_COLS),
         ("ngroups", C.c_int32), ("groups", C.c_int32 * MAX_KEYS),
         ("naggs", C.c_int32), ("aggs", AggCall * MAX_AGGS),
         ("expected_groups", C.c_int64),
+        ("n_derived", C.c_int32), ("derived", DerivedCol * MAX_DERIVED),
+        ("row_filter_col", C.c_int32), ("row_filter_op", C.c_int32), ("row_filter_value", C.c_int64),
     ]
 
 

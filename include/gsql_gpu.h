@@ -205,6 +205,21 @@ typedef struct gsql_agg_call {
     int32_t filter_arg; /* -1 = none (AggregateCall.filterArg) */
 } gsql_agg_call;
 
+/* Fused scan-side Project / Filter (the restricted forms TPC-H Q1 / Q3 need; replaces a VectorizedProjectExec /
+ * VectorizedFilterExec directly under the HashAgg — operator/VectorizedProjectExec.java:40-143).  A derived column is
+ * an FP64 value computed per row from FP64/INT input columns; it is NULL when any operand is NULL.  Aggregate calls
+ * address derived column i as column index n_input_cols + i. */
+typedef enum gsql_expr_kind {
+    GSQL_EXPR_MUL_1MINUS = 1,        /* a * (1 - b)            e.g. l_extendedprice * (1 - l_discount) */
+    GSQL_EXPR_MUL_1MINUS_1PLUS = 2   /* a * (1 - b) * (1 + c)  e.g. ... * (1 + l_tax) */
+} gsql_expr_kind;
+typedef struct gsql_derived_col {
+    int32_t kind; /* gsql_expr_kind */
+    int32_t a, b, c;
+} gsql_derived_col;
+typedef enum gsql_cmp_op { GSQL_CMP_NONE = 0, GSQL_CMP_LE = 1, GSQL_CMP_LT = 2, GSQL_CMP_GE = 3, GSQL_CMP_GT = 4, GSQL_CMP_EQ = 5, GSQL_CMP_NE = 6 } gsql_cmp_op;
+#define GSQL_MAX_DERIVED 4
+
 typedef struct gsql_agg_spec {
     int32_t n_input_cols;
     int32_t input_types[GSQL_MAX_COLS];
@@ -213,6 +228,13 @@ typedef struct gsql_agg_spec {
     int32_t naggs;
     gsql_agg_call aggs[GSQL_MAX_AGGS];
     int64_t expected_groups; /* planner estimate; only sizes the first table */
+    int32_t n_derived;
+    gsql_derived_col derived[GSQL_MAX_DERIVED];
+    /* row filter `input[row_filter_col] <op> row_filter_value` on an INT/BIGINT column; rows that fail (or are NULL
+     * there) are not aggregated.  GSQL_CMP_NONE = no filter. */
+    int32_t row_filter_col;
+    int32_t row_filter_op; /* gsql_cmp_op */
+    int64_t row_filter_value;
 } gsql_agg_spec;
 
 gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec, gsql_agg **out);

@@ -340,3 +340,59 @@ def test_all_to_all_single_rank(gu):
     assert recv.tolist() == [n]
     assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
     c.lib.gsql_comm_destroy(c.ptr)
+
+
+# ------------------------------------------------------------------------------------------------ low-cardinality / fused Q1 shape
+def test_agg_q1_shape_fused_project_filter(gu):
+    """TPC-H Q1 shape: 2 INT keys (3 x 2 values), fused derived columns price*(1-disc), price*(1-disc)*(1+tax) and the
+    shipdate predicate inside the aggregation kernel.  The oracle gets the same expressions precomputed with numpy."""
+    from galaxysql_b200 import api, native as N
+    n = 2_000_000
+    flag = (ku.rand_u64(n, 1) % np.uint64(3)).astype(np.int32)
+    status = (ku.rand_u64(n, 2) % np.uint64(2)).astype(np.int32)
+    qty = ((ku.rand_u64(n, 3) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
+    price = ((ku.rand_u64(n, 4) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    disc = (ku.rand_u64(n, 5) % np.uint64(11)).astype(np.float64) / 100.0
+    tax = (ku.rand_u64(n, 6) % np.uint64(9)).astype(np.float64) / 100.0
+    ship = ((ku.rand_u64(n, 7) % np.uint64(2526)) + np.uint64(8036)).astype(np.int32)
+    cutoff = 10471
+    qn = ku.with_nulls(qty, 0.01, 8)        # a few NULL measures too
+    cols = [(flag, None), (status, None), qn, (price, None), (disc, None), (tax, None), (ship, None)]
+    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [7]), (N.AGG_SUM, [8]), (N.AGG_AVG, [2]), (N.AGG_AVG, [3]),
+            (N.AGG_AVG, [4]), (N.AGG_COUNT_STAR, [])]
+    for mem in ("host", "device"):
+        a = api.HashAgg(gu.ctx(), [0, 0, 2, 2, 2, 2, 0], [0, 1], aggs, 1024,
+                        derived=[(N.EXPR_MUL_1MINUS, 3, 4, 0), (N.EXPR_MUL_1MINUS_1PLUS, 3, 4, 5)], row_filter=(6, N.CMP_LE, cutoff))
+        edges = [0, 700_000, n]
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            part = [(d[lo:hi], None if nl is None else nl[lo:hi]) for d, nl in cols]
+            a.consume(gu.to_device(part) if mem == "device" else part)
+        got = gu.to_numpy(a.result(N.MEM_DEVICE if mem == "device" else N.MEM_HOST))
+        a.close()
+        m = ship <= cutoff
+        e1 = price * (1.0 - disc)
+        e2 = e1 * (1.0 + tax)
+        ocols = [(flag[m], None), (status[m], None), (qn[0][m], qn[1][m]), (price[m], None), (disc[m], None), (e1[m], None), (e2[m], None)]
+        oaggs = [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_SUM, [5]), orc.AggCall(orc.AGG_SUM, [6]),
+                 orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_AVG, [3]), orc.AggCall(orc.AGG_AVG, [4]), orc.AggCall(orc.AGG_COUNT_STAR)]
+        exp = orc.hash_agg(ocols, [0, 1], oaggs, 1024)
+        assert len(got[0][0]) == 6
+        gu.approx_rows_equal(got, exp, float_cols=[2, 3, 4, 5, 6, 7, 8], key_cols=[0, 1], rtol=RTOL)
+
+
+def test_agg_smem_path_adapts_to_high_cardinality(gu):
+    """The shared-memory path must stay correct when the key set does not fit the CTA tables (rows bypass them)."""
+    n = 400_000
+    k = (ku.rand_u64(n, 21) % np.uint64(150_000)).astype(np.int64)
+    v = (ku.rand_u64(n, 22) % np.uint64(1000)).astype(np.float64)
+    w = (ku.rand_u64(n, 23) % np.uint64(1000)).astype(np.int64) - 500
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_MIN, [1]), orc.AggCall(orc.AGG_MAX, [2]),
+            orc.AggCall(orc.AGG_SUM0, [2]), orc.AggCall(orc.AGG_AVG, [1])]
+    cols = [(k, None), ku.with_nulls(v, 0.02, 24), (w, None)]
+    exp = orc.hash_agg(cols, [0], aggs, 1024)
+    got = gu.gpu_hash_agg(cols, [0], aggs, 1024, mem="device", batches=3)
+    gu.approx_rows_equal(got, exp, float_cols=[2, 6], key_cols=[0], rtol=RTOL)
+    # and the no-GROUP-BY form (one group, all rows in one CTA slot)
+    exp = orc.hash_agg(cols, [], aggs, 16)
+    got = gu.gpu_hash_agg(cols, [], aggs, 16, mem="device", batches=2)
+    gu.approx_rows_equal(got, exp, float_cols=[1, 5], key_cols=[], rtol=RTOL)
