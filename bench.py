@@ -150,8 +150,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "C2 inner hash join, BIGINT key + 2 INT payloads (CPU sample)", "build_rows": sb, "probe_rows": sp,
-                   "note": "reference Java cannot run (no JDK); oracle port in the reference's parallel shape"},
+        "config": {"workload": "C2: inner hash join 100M build x 1B probe, BIGINT key + 2 INT payloads" + (", 1 GPU" if args.gpus == 1 else f" per GPU x {args.gpus}"),
+                   "sample_build_rows": sb, "sample_probe_rows": sp,
+                   "note": "bounded sample of the workload per step on the host cores; the reference Java cannot run (no JDK in the "
+                           "image) so this is the oracle port in the reference's parallel shape (P drivers, 1000-row chunks, shared CAS table)"},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": host_threads(), "kind": "port",
                          "sample": f"{sb} build x {sp} probe rows per step, {host_threads()} threads, 1000-row chunks"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
