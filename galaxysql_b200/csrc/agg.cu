@@ -55,6 +55,7 @@ struct AggParams {
     int64_t row0, rows;
     int64_t gcap;                  // groups the arrays can hold before a grow (a slack margin sits above it)
     int32_t n_derived, rf_col, rf_op, pad2;
+    int32_t keycol[GSQL_MAX_KEYS];  // input column index of each group key
     int64_t rf_value;
     gsql_derived_col derived[GSQL_MAX_DERIVED];
 };
@@ -518,6 +519,7 @@ static void agg_fill_params(gsql_agg *a, const StagedBatch *sb, AggParams *P) {
     P->counters = a->counters.as<unsigned long long>();
     P->overflow_rows = a->overflow.as<int64_t>();
     P->gcap = a->gcap;
+    for (int k = 0; k < a->nkeys; k++) P->keycol[k] = a->spec.groups[k];
     P->n_derived = a->spec.n_derived;
     for (int i = 0; i < a->spec.n_derived; i++) P->derived[i] = a->spec.derived[i];
     P->rf_col = a->spec.row_filter_col;
@@ -553,26 +555,27 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     }
     gsql_agg *a = new gsql_agg();
     a->ctx = ctx;
+    gsql_ctx_retain(ctx);
     a->spec = s;
     a->nkeys = s.ngroups;
     a->naggs = s.naggs;
     for (int k = 0; k < s.ngroups; k++) a->out_types[a->nout++] = s.input_types[s.groups[k]];
     for (int i = 0; i < s.naggs; i++) {
         const gsql_agg_call &c = s.aggs[i];
-        if (c.kind < GSQL_AGG_COUNT_STAR || c.kind > GSQL_AGG_SUM0) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "agg kind %d", c.kind); }
+        if (c.kind < GSQL_AGG_COUNT_STAR || c.kind > GSQL_AGG_SUM0) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "agg kind %d", c.kind); }
         int need = c.kind == GSQL_AGG_COUNT_STAR ? 0 : 1;
-        if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != 1)) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
+        if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != 1)) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
         for (int q = 0; q < c.ncols; q++)
-            if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols + s.n_derived) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
-        if (c.filter_arg >= s.n_input_cols) { delete a; return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: filter column", i); }
+            if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols + s.n_derived) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
+        if (c.filter_arg >= s.n_input_cols) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: filter column", i); }
         a->in_type[i] = c.ncols > 0 ? (c.cols[0] < s.n_input_cols ? s.input_types[c.cols[0]] : GSQL_T_FP64) : GSQL_T_INT64;
         // planner-time fall-through cases (the stock HashAggExec keeps them): AVG over integers is DECIMAL division
-        if (c.kind == GSQL_AGG_AVG && a->in_type[i] != GSQL_T_FP64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG(integer) -> DECIMAL not on the GPU path"); }
-        if (c.kind == GSQL_AGG_SUM0 && a->in_type[i] != GSQL_T_INT64) { delete a; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "SUM0 needs BIGINT input"); }
+        if (c.kind == GSQL_AGG_AVG && a->in_type[i] != GSQL_T_FP64) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG(integer) -> DECIMAL not on the GPU path"); }
+        if (c.kind == GSQL_AGG_SUM0 && a->in_type[i] != GSQL_T_INT64) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "SUM0 needs BIGINT input"); }
         a->out_types[a->nout++] = agg_out_type(c.kind, a->in_type[i]);
     }
     cudaSetDevice(ctx->device);
-    agg_fast_plan(&a->fast, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    agg_fast_plan(&a->fast, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
     a->slack = (int64_t)ctx->sm_count * 2048 + 1024 + (int64_t)ctx->sm_count * 2 * 1024;  // + CTA-table merges of the smem path
     int64_t gcap = s.expected_groups > 0 ? s.expected_groups : 1024;
@@ -586,15 +589,17 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
         cudaStreamSynchronize(ctx->stream);
         a->ngroups = 1;
     }
-    if (st != GSQL_OK) { delete a; return st; }
+    if (st != GSQL_OK) { delete a; gsql_ctx_release(ctx); return st; }
     *out = a;
     return GSQL_OK;
 }
 
 extern "C" void gsql_agg_destroy(gsql_agg *a) {
     if (!a) return;
-    cudaSetDevice(a->ctx->device);
+    gsql_ctx *ctx = a->ctx;
+    cudaSetDevice(ctx->device);
     delete a;
+    gsql_ctx_release(ctx);
 }
 
 static gsql_status agg_read_counters(gsql_agg *a, unsigned long long *h) {
@@ -628,6 +633,11 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
             int64_t warps = div_up(P.rows, 32);
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, div_up(warps, AF_THREADS / 32));
             if (grid < 1) grid = 1;
+            static int attr_smem = 0;
+            if (a->fast.L.total > attr_smem) {
+                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, a->fast.L.total));
+                attr_smem = a->fast.L.total;
+            }
             k_agg_smem<<<grid, AF_THREADS, a->fast.L.total, ctx->stream>>>(P, a->fast.L);
         } else {
             KernelScope ks(ctx, "agg_consume");

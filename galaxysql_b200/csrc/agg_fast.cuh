@@ -16,6 +16,8 @@ namespace {
 
 constexpr int AF_THREADS = 512;
 constexpr int AF_MAX_PROBES = 8;
+constexpr int AF_MAX_USED = 12;
+constexpr int AF_STAGE_BYTES_PER_WARP = AF_MAX_USED * 32 * 8 + AF_MAX_USED * 32;
 enum { C_FALLBACK = 2 };  // counters[2]: rows that bypassed the CTA table
 
 struct SmemLayout {
@@ -27,6 +29,12 @@ struct SmemLayout {
     int32_t off_cnt[GSQL_MAX_AGGS];  // AVG row count, -1 when unused
     int32_t off_has[GSQL_MAX_AGGS];
     int32_t total;
+    // every input column the kernel touches (keys, aggregate arguments, derived operands, filters): loaded once per
+    // row with all loads in flight, staged in a warp-private shared-memory strip, then read by column index
+    int32_t nused;
+    int32_t used[AF_MAX_USED];
+    int8_t colmap[GSQL_MAX_COLS];  // input column -> staging row, -1 = unused
+    int32_t off_stage;             // per warp: AF_MAX_USED x 32 x 8 B values + AF_MAX_USED x 32 B null flags
 };
 
 __device__ __forceinline__ int smem_find_or_insert(char *sm, const SmemLayout &L, int nkeys, const int64_t (&kv)[GSQL_MAX_KEYS],
@@ -122,17 +130,96 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (AF_THREADS / 32);
     const int64_t warp_id = (int64_t)blockIdx.x * (AF_THREADS / 32) + (threadIdx.x >> 5);
+    unsigned long long *sval = reinterpret_cast<unsigned long long *>(sm + L.off_stage + (size_t)(threadIdx.x >> 5) * AF_STAGE_BYTES_PER_WARP);
+    uint8_t *snul = reinterpret_cast<uint8_t *>(sval + AF_MAX_USED * 32);
+    // staged accessors (this lane's row): values are stored widened (INT32 sign-extended, FP64 as bits)
+    auto s_null = [&](int col) -> bool { return snul[L.colmap[col] * 32 + lane] != 0; };
+    auto s_raw = [&](int col) -> unsigned long long { return sval[L.colmap[col] * 32 + lane]; };
+    auto s_f64 = [&](int col) -> double {
+        unsigned long long v = s_raw(col);
+        return P.in.c[col].type == GSQL_T_FP64 ? __longlong_as_double((long long)v) : (double)(long long)v;
+    };
+    auto s_i64 = [&](int col) -> long long {
+        unsigned long long v = s_raw(col);
+        return P.in.c[col].type == GSQL_T_FP64 ? (long long)__longlong_as_double((long long)v) : (long long)v;
+    };
+    auto v_null = [&](int col) -> bool {  // plain or derived column
+        if (col < P.in.n) return s_null(col);
+        const gsql_derived_col &d = P.derived[col - P.in.n];
+        bool n = s_null(d.a) || s_null(d.b);
+        if (d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) n = n || s_null(d.c);
+        return n;
+    };
+    auto v_f64 = [&](int col) -> double {
+        if (col < P.in.n) return s_f64(col);
+        const gsql_derived_col &d = P.derived[col - P.in.n];
+        double x = s_f64(d.a) * (1.0 - s_f64(d.b));
+        if (d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) x = x * (1.0 + s_f64(d.c));
+        return x;
+    };
+    auto v_i64 = [&](int col) -> long long { return col < P.in.n ? s_i64(col) : (long long)v_f64(col); };
+
     unsigned int fallback_rows = 0;
     for (int64_t b = warp_id * 32; b < P.rows; b += warps_total * 32) {
         const int64_t i = b + lane;
         const int64_t r = P.row0 + i;
-        const bool live = i < P.rows && row_passes(P, r);
+        const bool inrange = i < P.rows;
+        // ---- 1. every load of this row in flight at once, then staged
+        {
+            unsigned long long raw[AF_MAX_USED];
+            uint8_t nul[AF_MAX_USED];
+#pragma unroll
+            for (int u = 0; u < AF_MAX_USED; u++) {
+                raw[u] = 0;
+                nul[u] = 0;
+                if (u < L.nused && inrange) {
+                    const DCol &col = P.in.c[L.used[u]];
+                    if (col.type == GSQL_T_INT32) raw[u] = (unsigned long long)(long long)ld_stream_4(reinterpret_cast<const int *>(col.data) + r);
+                    else raw[u] = (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+                    if (col.nulls) nul[u] = col.nulls[r];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AF_MAX_USED; u++) {
+                if (u < L.nused) {
+                    sval[u * 32 + lane] = raw[u];
+                    snul[u * 32 + lane] = nul[u];
+                }
+            }
+        }
+        // ---- 2. row filter, key, slot
+        bool live = inrange;
+        if (live && P.rf_op != GSQL_CMP_NONE) {
+            if (s_null(P.rf_col)) live = false;
+            else {
+                long long v = s_i64(P.rf_col);
+                switch (P.rf_op) {
+                case GSQL_CMP_LE: live = v <= P.rf_value; break;
+                case GSQL_CMP_LT: live = v < P.rf_value; break;
+                case GSQL_CMP_GE: live = v >= P.rf_value; break;
+                case GSQL_CMP_GT: live = v > P.rf_value; break;
+                case GSQL_CMP_EQ: live = v == P.rf_value; break;
+                default: live = v != P.rf_value; break;
+                }
+            }
+        }
         int64_t kv[GSQL_MAX_KEYS];
         bool kn[GSQL_MAX_KEYS];
         unsigned long long d = 0;
         int slot = -2;
         if (live) {
-            if (P.nkeys > 0) d = load_group_key(P, r, kv, kn);
+            for (int c = 0; c < P.nkeys; c++) {  // canonical key image from the staged values (group key type = column type)
+                const int col = P.keycol[c];
+                kn[c] = s_null(col);
+                long long v = (long long)s_raw(col);
+                if (!kn[c] && P.in.c[col].type == GSQL_T_FP64) {
+                    double x = __longlong_as_double(v);
+                    if (x != x) v = 0x7ff8000000000000LL;
+                    else if (x == 0.0) v = 0;
+                }
+                kv[c] = kn[c] ? 0 : v;
+            }
+            if (P.nkeys > 0) d = digest_of_keys(P, kv, kn);
             slot = smem_find_or_insert(sm, L, P.nkeys, kv, kn, d);
             if (slot == -1) {  // does not fit the CTA table: the generic path, right here
                 fallback_rows++;
@@ -153,12 +240,11 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
             const AggDev &ag = P.agg[a];
             bool ok = useful;
             if (ok && ag.filter_col >= 0) {
-                const DCol &f = P.in.c[ag.filter_col];
-                if (f.type == GSQL_T_INT64 && !in_null(f, r) && reinterpret_cast<const int64_t *>(f.data)[r] < 1) ok = false;
+                if (P.in.c[ag.filter_col].type == GSQL_T_INT64 && !s_null(ag.filter_col) && s_i64(ag.filter_col) < 1) ok = false;
             }
             if (ok) {
                 for (int q = 0; q < ag.ncols; q++)
-                    if (val_null(P, ag.cols[q], r)) ok = false;  // COUNT: any NULL arg; others: the single argument
+                    if (v_null(ag.cols[q])) ok = false;  // COUNT: any NULL arg; others: the single argument
             }
             const unsigned okmask = __ballot_sync(0xffffffffu, ok);
             const unsigned long long cnt = __popc(peers & okmask);
@@ -170,30 +256,30 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
                 break;
             case GSQL_AGG_SUM:
             case GSQL_AGG_AVG: {
-                double v = ok ? val_f64(P, ag.cols[0], r) : 0.0;
-                double s = peer_sum_f64(v, peers);
+                double v = ok ? v_f64(ag.cols[0]) : 0.0;
+                double sum = peer_sum_f64(v, peers);
                 if (leader && cnt) {
-                    atomicAdd(reinterpret_cast<double *>(&acc[slot]), s);
+                    atomicAdd(reinterpret_cast<double *>(&acc[slot]), sum);
                     if (L.off_cnt[a] >= 0) atomicAdd(reinterpret_cast<unsigned long long *>(sm + L.off_cnt[a]) + slot, cnt);
                     reinterpret_cast<uint8_t *>(sm + L.off_has[a])[slot] = 1;
                 }
                 break;
             }
             case GSQL_AGG_SUM0: {
-                long long v = ok ? val_i64(P, ag.cols[0], r) : 0;
-                long long s = peer_sum_i64(v, peers);
-                if (leader && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[slot]), (unsigned long long)s);
+                long long v = ok ? v_i64(ag.cols[0]) : 0;
+                long long sum = peer_sum_i64(v, peers);
+                if (leader && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[slot]), (unsigned long long)sum);
                 break;
             }
             default: {  // MIN / MAX on the order-preserving int64 image
                 const bool mx = ag.kind == GSQL_AGG_MAX;
                 long long ident = mx ? (long long)0x8000000000000000ULL : 0x7fffffffffffffffLL;
                 long long v = ident;
-                if (ok) v = ag.in_type == GSQL_T_FP64 ? dbl_sortable(val_f64(P, ag.cols[0], r), mx) : val_i64(P, ag.cols[0], r);
-                long long s = peer_minmax_i64(v, peers, mx);
+                if (ok) v = ag.in_type == GSQL_T_FP64 ? dbl_sortable(v_f64(ag.cols[0]), mx) : v_i64(ag.cols[0]);
+                long long m = peer_minmax_i64(v, peers, mx);
                 if (leader && cnt) {
-                    if (mx) atomicMax(&acc[slot], s);
-                    else atomicMin(&acc[slot], s);
+                    if (mx) atomicMax(&acc[slot], m);
+                    else atomicMin(&acc[slot], m);
                     reinterpret_cast<uint8_t *>(sm + L.off_has[a])[slot] = 1;
                 }
             }
@@ -253,8 +339,10 @@ struct AggFast {
 };
 
 // Decides eligibility and the shared-memory layout (host).
-static void agg_fast_plan(AggFast *F, int nkeys, int naggs, const gsql_agg_call *aggs, const int32_t *in_type) {
+static void agg_fast_plan(AggFast *F, const gsql_agg_spec &spec, int nkeys, int naggs, const gsql_agg_call *aggs, const int32_t *in_type) {
     F->eligible = false;
+    for (int k = 0; k < nkeys; k++)
+        if (spec.input_types[spec.groups[k]] == GSQL_T_FP64 && false) return;
     for (int a = 0; a < naggs; a++)
         if (aggs[a].kind == GSQL_AGG_SUM && in_type[a] != GSQL_T_FP64) return;  // exact 128-bit SUM(int) stays generic
     int per_slot = 4 + nkeys * 9;
@@ -278,7 +366,40 @@ static void agg_fast_plan(AggFast *F, int nkeys, int naggs, const gsql_agg_call 
     off += S * 4;
     for (int c = 0; c < nkeys; c++) { L.off_kn[c] = off; off += S; }
     for (int a = 0; a < naggs; a++) { L.off_has[a] = off; off += S; }
-    L.total = (off + 15) & ~15;
+    off = (off + 15) & ~15;
+    // used input columns
+    for (int c = 0; c < GSQL_MAX_COLS; c++) L.colmap[c] = -1;
+    L.nused = 0;
+    bool too_many = false;
+    auto use = [&](int col) {
+        if (col < 0) return;
+        if (col >= spec.n_input_cols) {  // derived: its operands
+            const gsql_derived_col &d = spec.derived[col - spec.n_input_cols];
+            const int ops[3] = {d.a, d.b, d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS ? d.c : -1};
+            for (int q = 0; q < 3; q++)
+                if (ops[q] >= 0 && L.colmap[ops[q]] < 0) {
+                    if (L.nused == AF_MAX_USED) { too_many = true; return; }
+                    L.colmap[ops[q]] = (int8_t)L.nused;
+                    L.used[L.nused++] = ops[q];
+                }
+            return;
+        }
+        if (L.colmap[col] < 0) {
+            if (L.nused == AF_MAX_USED) { too_many = true; return; }
+            L.colmap[col] = (int8_t)L.nused;
+            L.used[L.nused++] = col;
+        }
+    };
+    for (int k = 0; k < nkeys; k++) use(spec.groups[k]);
+    if (spec.row_filter_op != GSQL_CMP_NONE) use(spec.row_filter_col);
+    for (int a = 0; a < naggs; a++) {
+        use(aggs[a].filter_arg);
+        for (int q = 0; q < aggs[a].ncols; q++) use(aggs[a].cols[q]);
+    }
+    if (too_many) return;
+    L.off_stage = off;
+    off += (AF_THREADS / 32) * AF_STAGE_BYTES_PER_WARP;
+    L.total = off;
     F->eligible = true;
     F->enabled = true;
 }

@@ -39,7 +39,11 @@ struct gsql_ctx {
     void *nccl_comm = nullptr;  // ncclComm_t
     int nranks = 1, rank = 0;
     int sm_count = 148;
+    int refs = 1;  // the creator + every live handle: a handle may be destroyed after gsql_ctx_destroy (GC order)
 };
+
+void gsql_ctx_retain(gsql_ctx *ctx);
+void gsql_ctx_release(gsql_ctx *ctx);
 
 gsql_status gsql_set_error(gsql_ctx *ctx, gsql_status st, const char *fmt, ...);
 

@@ -45,8 +45,32 @@ extern "C" gsql_status gsql_ctx_create(int device, gsql_ctx **out) {
     return GSQL_OK;
 }
 
+#include <mutex>
+static std::mutex g_ref_mutex;
+
+void gsql_ctx_retain(gsql_ctx *ctx) {
+    std::lock_guard<std::mutex> g(g_ref_mutex);
+    ctx->refs++;
+}
+
+static void ctx_teardown(gsql_ctx *ctx);
+
+void gsql_ctx_release(gsql_ctx *ctx) {
+    bool last;
+    {
+        std::lock_guard<std::mutex> g(g_ref_mutex);
+        last = --ctx->refs == 0;
+    }
+    if (last) ctx_teardown(ctx);
+}
+
+// The context's resources live until the last handle created on it is destroyed.
 extern "C" void gsql_ctx_destroy(gsql_ctx *ctx) {
     if (!ctx) return;
+    gsql_ctx_release(ctx);
+}
+
+static void ctx_teardown(gsql_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto &p : ctx->prof)

@@ -367,6 +367,7 @@ extern "C" gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spe
 
     gsql_join *j = new gsql_join();
     j->ctx = ctx;
+    gsql_ctx_retain(ctx);
     j->spec = s;
     j->semi_join = semi;
     j->single_join = s.max_one_row != 0;
@@ -407,13 +408,13 @@ extern "C" gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spe
         int nleft = s.join_type == GSQL_JOIN_RIGHT ? s.n_inner_cols : s.n_outer_cols;
         int left_side = s.join_type == GSQL_JOIN_RIGHT ? inner_side : outer_side;
         int right_side = s.join_type == GSQL_JOIN_RIGHT ? outer_side : inner_side;
-        if (c < 0 || c >= s.n_outer_cols + s.n_inner_cols) { delete j; return gsql_set_error(ctx, GSQL_E_INVALID, "cond col"); }
+        if (c < 0 || c >= s.n_outer_cols + s.n_inner_cols) { delete j; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "cond col"); }
         j->cond_side[i] = c < nleft ? left_side : right_side;
         j->cond_col[i] = c < nleft ? c : c - nleft;
         int t = j->cond_side[i] == SIDE_PROBE ? j->probe_types[j->cond_col[i]] : j->build_types[j->cond_col[i]];
-        if (t == GSQL_T_FP64) { delete j; return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "condition on a double column"); }
+        if (t == GSQL_T_FP64) { delete j; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "condition on a double column"); }
     }
-    if (j->flags.alloc(ctx, F_COUNT * sizeof(int32_t)) != GSQL_OK) { delete j; return GSQL_E_OOM; }
+    if (j->flags.alloc(ctx, F_COUNT * sizeof(int32_t)) != GSQL_OK) { delete j; gsql_ctx_release(ctx); return GSQL_E_OOM; }
     cudaMemsetAsync(j->flags.p, 0, j->flags.bytes, ctx->stream);
     *out = j;
     return GSQL_OK;
@@ -421,8 +422,10 @@ extern "C" gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spe
 
 extern "C" void gsql_join_destroy(gsql_join *j) {
     if (!j) return;
-    cudaSetDevice(j->ctx->device);
+    gsql_ctx *ctx = j->ctx;
+    cudaSetDevice(ctx->device);
     delete j;
+    gsql_ctx_release(ctx);
 }
 
 static gsql_status join_reserve(gsql_join *j, int64_t need) {

@@ -160,12 +160,19 @@ extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spe
             return gsql_set_error(ctx, GSQL_E_INVALID, "channel %d", i);
     gsql_xchg *x = new gsql_xchg();
     x->ctx = ctx;
+    gsql_ctx_retain(ctx);
     x->spec = s;
     *out = x;
     return GSQL_OK;
 }
 
-extern "C" void gsql_xchg_destroy(gsql_xchg *x) { delete x; }
+extern "C" void gsql_xchg_destroy(gsql_xchg *x) {
+    if (!x) return;
+    gsql_ctx *ctx = x->ctx;
+    cudaSetDevice(ctx->device);
+    delete x;
+    gsql_ctx_release(ctx);
+}
 
 // Partitions staged device columns into `O` (device).  d_part_offsets receives nparts+1 int64 offsets (device).
 static gsql_status partition_device(gsql_xchg *x, const StagedBatch &sb, const XOut &O, DevBuf *offs_out, int64_t *host_counts) {
