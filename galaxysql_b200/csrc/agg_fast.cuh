@@ -1,10 +1,12 @@
 // agg_fast.cuh — shared-memory privatised group-by for low-cardinality keys (the TPC-H Q1 shape), included by agg.cu.
 //
-// Every CTA owns a small open-addressing table {key values, NULL flags, accumulators} in shared memory.  A warp
-// step takes 32 rows: each lane finds (or inserts) its key's slot in the CTA table, lanes with the same slot are
-// grouped with __match_any_sync, the group's values are reduced inside the warp, and ONE lane per distinct key
-// updates the shared-memory accumulators — so 600 M rows x 8 accumulators never touch an L2 atomic.  When the CTA
-// finishes its rows the <= S partial groups are merged into the global table (find_group_kv + global atomics).
+// Every WARP owns a small open-addressing table {key values, NULL flags, accumulators} in shared memory.  A warp
+// step takes 32 rows: all the row's input columns are loaded with every load in flight and staged in a warp-private
+// strip; each lane finds (or inserts) its key's slot in the warp table, lanes with the same slot are grouped with
+// __match_any_sync, the group's values are reduced inside the warp with shuffles, and ONE lane per distinct key
+// updates the accumulators with plain read-modify-writes — no atomics at all on the hot path (a CTA-shared table
+// with shared-memory fp64 atomics measured 12.6 G rows/s on the Q1 shape: CAS-loop contention on 6 hot slots).
+// When a warp finishes its rows its <= S partial groups are merged into the global table (find_group_kv + L2 atomics).
 // The path is adaptive: a row whose key does not fit the CTA table (table full / more than 8 probes) goes through the
 // generic global path on the spot, and the host stops using this kernel when too many rows do that.
 //
@@ -16,7 +18,7 @@ namespace {
 
 constexpr int AF_THREADS = 512;
 constexpr int AF_MAX_PROBES = 8;
-constexpr int AF_MAX_USED = 12;
+constexpr int AF_MAX_USED = 8;
 constexpr int AF_STAGE_BYTES_PER_WARP = AF_MAX_USED * 32 * 8 + AF_MAX_USED * 32;
 enum { C_FALLBACK = 2 };  // counters[2]: rows that bypassed the CTA table
 
@@ -34,7 +36,8 @@ struct SmemLayout {
     int32_t nused;
     int32_t used[AF_MAX_USED];
     int8_t colmap[GSQL_MAX_COLS];  // input column -> staging row, -1 = unused
-    int32_t off_stage;             // per warp: AF_MAX_USED x 32 x 8 B values + AF_MAX_USED x 32 B null flags
+    int32_t off_stage;             // AF_MAX_USED x 32 x 8 B values + AF_MAX_USED x 32 B null flags
+    int32_t warp_bytes;            // table + staging strip of one warp
 };
 
 __device__ __forceinline__ int smem_find_or_insert(char *sm, const SmemLayout &L, int nkeys, const int64_t (&kv)[GSQL_MAX_KEYS],
@@ -114,9 +117,12 @@ __device__ __forceinline__ long long peer_minmax_i64(long long v, unsigned peers
 }
 
 __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constant__ AggParams P, const __grid_constant__ SmemLayout L) {
-    extern __shared__ __align__(16) char sm[];
-    // ---- init the CTA table
-    for (int i = threadIdx.x; i < L.S; i += AF_THREADS) {
+    extern __shared__ __align__(16) char sm_all[];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_cta = threadIdx.x >> 5;
+    char *sm = sm_all + (size_t)warp_in_cta * L.warp_bytes;  // this warp's table + staging strip
+    // ---- init the warp table
+    for (int i = lane; i < L.S; i += 32) {
         reinterpret_cast<int *>(sm + L.off_state)[i] = P.nkeys == 0 ? 2 : 0;
         for (int a = 0; a < P.naggs; a++) {
             long long init = P.agg[a].kind == GSQL_AGG_MIN ? 0x7fffffffffffffffLL : P.agg[a].kind == GSQL_AGG_MAX ? (long long)0x8000000000000000ULL : 0;
@@ -125,12 +131,11 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
             reinterpret_cast<uint8_t *>(sm + L.off_has[a])[i] = 0;
         }
     }
-    __syncthreads();
+    __syncwarp();
 
-    const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (AF_THREADS / 32);
     const int64_t warp_id = (int64_t)blockIdx.x * (AF_THREADS / 32) + (threadIdx.x >> 5);
-    unsigned long long *sval = reinterpret_cast<unsigned long long *>(sm + L.off_stage + (size_t)(threadIdx.x >> 5) * AF_STAGE_BYTES_PER_WARP);
+    unsigned long long *sval = reinterpret_cast<unsigned long long *>(sm + L.off_stage);
     uint8_t *snul = reinterpret_cast<uint8_t *>(sval + AF_MAX_USED * 32);
     // staged accessors (this lane's row): values are stored widened (INT32 sign-extended, FP64 as bits)
     auto s_null = [&](int col) -> bool { return snul[L.colmap[col] * 32 + lane] != 0; };
@@ -252,15 +257,15 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
             switch (ag.kind) {
             case GSQL_AGG_COUNT_STAR:
             case GSQL_AGG_COUNT:
-                if (leader && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[slot]), cnt);
+                if (leader && cnt) acc[slot] += (long long)cnt;
                 break;
             case GSQL_AGG_SUM:
             case GSQL_AGG_AVG: {
                 double v = ok ? v_f64(ag.cols[0]) : 0.0;
                 double sum = peer_sum_f64(v, peers);
                 if (leader && cnt) {
-                    atomicAdd(reinterpret_cast<double *>(&acc[slot]), sum);
-                    if (L.off_cnt[a] >= 0) atomicAdd(reinterpret_cast<unsigned long long *>(sm + L.off_cnt[a]) + slot, cnt);
+                    reinterpret_cast<double *>(acc)[slot] += sum;
+                    if (L.off_cnt[a] >= 0) reinterpret_cast<long long *>(sm + L.off_cnt[a])[slot] += (long long)cnt;
                     reinterpret_cast<uint8_t *>(sm + L.off_has[a])[slot] = 1;
                 }
                 break;
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
             case GSQL_AGG_SUM0: {
                 long long v = ok ? v_i64(ag.cols[0]) : 0;
                 long long sum = peer_sum_i64(v, peers);
-                if (leader && cnt) atomicAdd(reinterpret_cast<unsigned long long *>(&acc[slot]), (unsigned long long)sum);
+                if (leader && cnt) acc[slot] = (long long)((unsigned long long)acc[slot] + (unsigned long long)sum);
                 break;
             }
             default: {  // MIN / MAX on the order-preserving int64 image
@@ -278,18 +283,18 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
                 if (ok) v = ag.in_type == GSQL_T_FP64 ? dbl_sortable(v_f64(ag.cols[0]), mx) : v_i64(ag.cols[0]);
                 long long m = peer_minmax_i64(v, peers, mx);
                 if (leader && cnt) {
-                    if (mx) atomicMax(&acc[slot], m);
-                    else atomicMin(&acc[slot], m);
+                    acc[slot] = mx ? (m > acc[slot] ? m : acc[slot]) : (m < acc[slot] ? m : acc[slot]);
                     reinterpret_cast<uint8_t *>(sm + L.off_has[a])[slot] = 1;
                 }
             }
             }
         }
+        __syncwarp();  // the next step's leaders (other lanes) read-modify-write the same accumulators
     }
     if (fallback_rows) atomicAdd(&P.counters[C_FALLBACK], (unsigned long long)fallback_rows);
-    __syncthreads();
-    // ---- merge the CTA's partial groups into the global table
-    for (int s = threadIdx.x; s < L.S; s += AF_THREADS) {
+    __syncwarp();
+    // ---- merge this warp's partial groups into the global table
+    for (int s = lane; s < L.S; s += 32) {
         if (reinterpret_cast<int *>(sm + L.off_state)[s] != 2) continue;
         int64_t kv[GSQL_MAX_KEYS];
         bool kn[GSQL_MAX_KEYS];
@@ -348,10 +353,7 @@ static void agg_fast_plan(AggFast *F, const gsql_agg_spec &spec, int nkeys, int 
     int per_slot = 4 + nkeys * 9;
     for (int a = 0; a < naggs; a++) per_slot += 8 + 1 + (aggs[a].kind == GSQL_AGG_AVG ? 8 : 0);
     int S = 1;
-    if (nkeys > 0) {
-        S = 1024;
-        while (S > 16 && (size_t)S * per_slot > 40 * 1024) S >>= 1;
-    }
+    if (nkeys > 0) S = per_slot <= 160 ? 32 : 16;  // slots of one WARP's table; more distinct keys bypass it (adaptive)
     SmemLayout &L = F->L;
     memset(&L, 0, sizeof(L));
     L.S = S;
@@ -398,8 +400,9 @@ static void agg_fast_plan(AggFast *F, const gsql_agg_spec &spec, int nkeys, int 
     }
     if (too_many) return;
     L.off_stage = off;
-    off += (AF_THREADS / 32) * AF_STAGE_BYTES_PER_WARP;
-    L.total = off;
+    off += AF_STAGE_BYTES_PER_WARP;
+    L.warp_bytes = (off + 15) & ~15;
+    L.total = L.warp_bytes * (AF_THREADS / 32);
     F->eligible = true;
     F->enabled = true;
 }
