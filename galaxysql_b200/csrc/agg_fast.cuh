@@ -19,6 +19,7 @@ namespace {
 constexpr int AF_THREADS = 512;
 constexpr int AF_MAX_PROBES = 8;
 constexpr int AF_MAX_USED = 8;
+constexpr int AF_MAX_FV = 8;
 constexpr int AF_STAGE_BYTES_PER_WARP = AF_MAX_USED * 32 * 8 + AF_MAX_USED * 32;
 enum { C_FALLBACK = 2 };  // counters[2]: rows that bypassed the CTA table
 
@@ -38,6 +39,9 @@ struct SmemLayout {
     int8_t colmap[GSQL_MAX_COLS];  // input column -> staging row, -1 = unused
     int32_t off_stage;             // AF_MAX_USED x 32 x 8 B values + AF_MAX_USED x 32 B null flags
     int32_t warp_bytes;            // table + staging strip of one warp
+    int32_t nfv;                   // fp64 SUM / AVG aggregates reduced together in ONE peer loop (<= AF_MAX_FV)
+    int32_t fv_agg[AF_MAX_FV];
+    int8_t fused[GSQL_MAX_AGGS];   // 1 = this aggregate is one of fv_agg
 };
 
 __device__ __forceinline__ int smem_find_or_insert(char *sm, const SmemLayout &L, int nkeys, const int64_t (&kv)[GSQL_MAX_KEYS],
@@ -88,6 +92,25 @@ __device__ __forceinline__ double peer_sum_f64(double v, unsigned peers) {
         }
     }
     return s;
+}
+// Fused form: NV values reduced over the same peer groups with one pass over the peer bits.
+template <int NV>
+__device__ __forceinline__ void peer_sum_f64_multi(const double (&v)[NV], int nv, unsigned peers, double (&out)[NV]) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) out[j] = 0.0;
+    unsigned rem = peers;
+    while (__any_sync(0xffffffffu, rem != 0)) {
+        const int src = rem ? __ffs(rem) - 1 : 0;
+        const bool take = rem != 0;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            if (j < nv) {  // warp-uniform
+                double x = __shfl_sync(0xffffffffu, v[j], src);
+                if (take) out[j] += x;
+            }
+        }
+        rem &= rem - 1;
+    }
 }
 __device__ __forceinline__ long long peer_sum_i64(long long v, unsigned peers) {
     long long s = 0;
@@ -240,9 +263,40 @@ __global__ void __launch_bounds__(AF_THREADS, 2) k_agg_smem(const __grid_constan
         const bool useful = slot >= 0;
         const unsigned peers = __match_any_sync(0xffffffffu, slot);
         const bool leader = useful && lane == __ffs(peers) - 1;
+        // fp64 SUM / AVG arguments of all aggregates, reduced over the peer groups in one pass
+        double fv[AF_MAX_FV], fsum[AF_MAX_FV];
+        unsigned fokmask[AF_MAX_FV];
+#pragma unroll
+        for (int j = 0; j < AF_MAX_FV; j++) {
+            fv[j] = 0.0;
+            fokmask[j] = 0;
+            if (j < L.nfv) {
+                const AggDev &ag = P.agg[L.fv_agg[j]];
+                bool ok = useful;
+                if (ok && ag.filter_col >= 0)
+                    if (P.in.c[ag.filter_col].type == GSQL_T_INT64 && !s_null(ag.filter_col) && s_i64(ag.filter_col) < 1) ok = false;
+                if (ok && v_null(ag.cols[0])) ok = false;
+                if (ok) fv[j] = v_f64(ag.cols[0]);
+                fokmask[j] = __ballot_sync(0xffffffffu, ok);
+            }
+        }
+        peer_sum_f64_multi<AF_MAX_FV>(fv, L.nfv, peers, fsum);
+#pragma unroll
+        for (int j = 0; j < AF_MAX_FV; j++) {
+            if (j < L.nfv) {
+                const int a = L.fv_agg[j];
+                const unsigned long long cnt = __popc(peers & fokmask[j]);
+                if (leader && cnt) {
+                    reinterpret_cast<double *>(sm + L.off_acc[a])[slot] += fsum[j];
+                    if (L.off_cnt[a] >= 0) reinterpret_cast<long long *>(sm + L.off_cnt[a])[slot] += (long long)cnt;
+                    reinterpret_cast<uint8_t *>(sm + L.off_has[a])[slot] = 1;
+                }
+            }
+        }
 #pragma unroll 1
         for (int a = 0; a < P.naggs; a++) {
             const AggDev &ag = P.agg[a];
+            if (L.fused[a]) continue;  // handled above
             bool ok = useful;
             if (ok && ag.filter_col >= 0) {
                 if (P.in.c[ag.filter_col].type == GSQL_T_INT64 && !s_null(ag.filter_col) && s_i64(ag.filter_col) < 1) ok = false;
@@ -399,6 +453,14 @@ static void agg_fast_plan(AggFast *F, const gsql_agg_spec &spec, int nkeys, int 
         for (int q = 0; q < aggs[a].ncols; q++) use(aggs[a].cols[q]);
     }
     if (too_many) return;
+    L.nfv = 0;
+    for (int a = 0; a < naggs; a++) {
+        L.fused[a] = 0;
+        if ((aggs[a].kind == GSQL_AGG_SUM || aggs[a].kind == GSQL_AGG_AVG) && L.nfv < AF_MAX_FV) {
+            L.fused[a] = 1;
+            L.fv_agg[L.nfv++] = a;
+        }
+    }
     L.off_stage = off;
     off += AF_STAGE_BYTES_PER_WARP;
     L.warp_bytes = (off + 15) & ~15;
