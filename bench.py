@@ -177,6 +177,10 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # the AllToAllv is a grouped ncclSend/ncclRecv per peer: give the p2p path all the channels NVLink can use
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_P2P_NET_CHUNKSIZE", "4194304")
         dist.init_process_group("nccl", device_id=dev)
     ctx = api.Context(local_rank)
     stream = ctx.torch_stream()
