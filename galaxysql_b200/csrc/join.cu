@@ -951,9 +951,9 @@ static bool fast_probe_applicable(gsql_join *j, const gsql_batch *probe, const g
     if (out_capacity < probe->rows) return false;  // <= 1 output row per probe row; smaller buffers take the exact two-pass path
     for (int i = 0; i < probe->ncols; i++)
         if (probe->cols[i].nulls) return false;
-    if (out->mem == GSQL_MEM_DEVICE)  // the flush uses 16-byte stores: caller buffers must be 16-byte aligned
+    if (out->mem == GSQL_MEM_DEVICE)  // natural alignment of the caller's columns is enough (the flush aligns by address)
         for (int q = 0; q < j->nout; q++)
-            if (((uintptr_t)out->cols[q].data & 15) != 0) return false;
+            if (((uintptr_t)out->cols[q].data & (uintptr_t)(gsql_type_width(j->out_types[q]) - 1)) != 0) return false;
     if (j->outer_join)
         for (int q = 0; q < j->nout; q++)
             if (j->out_side[q] == SIDE_BUILD && !out->cols[q].nulls) {

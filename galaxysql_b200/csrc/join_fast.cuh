@@ -457,11 +457,12 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
         if (O.is32[q]) {
             const unsigned int *s32 = reinterpret_cast<const unsigned int *>(src) + (O.half[q] == 1 ? 1 : 0);  // element i at s32[2*i]
             int *dst = reinterpret_cast<int *>(O.data[q]);
-            const unsigned long long g0 = base & ~3ULL;
-            const unsigned int groups = (unsigned int)((end - g0 + 3) >> 2);
+            // groups of 4 elements whose ADDRESS is 16-byte aligned (the column base only needs natural alignment)
+            const long long g0 = (long long)base - (long long)((((unsigned long long)(uintptr_t)dst >> 2) + base) & 3ULL);
+            const unsigned int groups = (unsigned int)(((long long)end - g0 + 3) >> 2);
             for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
-                const unsigned long long g = g0 + 4ULL * grp;
-                if (g >= base && g + 4 <= end) {
+                const long long g = g0 + 4LL * grp;
+                if (g >= (long long)base && g + 4 <= (long long)end) {
                     const unsigned int l = (unsigned int)(g - base);
                     int4 v;
                     v.x = (int)s32[2 * l];
@@ -472,17 +473,17 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        if (g + i >= base && g + i < end) st_stream_4(dst + g + i, (int)s32[2 * (unsigned int)(g + i - base)]);
+                        if (g + i >= (long long)base && g + i < (long long)end) st_stream_4(dst + g + i, (int)s32[2 * (unsigned int)(g + i - (long long)base)]);
                 }
             }
         } else {
             const unsigned long long *s64 = reinterpret_cast<const unsigned long long *>(src);
             long long *dst = reinterpret_cast<long long *>(O.data[q]);
-            const unsigned long long g0 = base & ~1ULL;
-            const unsigned int groups = (unsigned int)((end - g0 + 1) >> 1);
+            const long long g0 = (long long)base - (long long)((((unsigned long long)(uintptr_t)dst >> 3) + base) & 1ULL);
+            const unsigned int groups = (unsigned int)(((long long)end - g0 + 1) >> 1);
             for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
-                const unsigned long long g = g0 + 2ULL * grp;
-                if (g >= base && g + 2 <= end) {
+                const long long g = g0 + 2LL * grp;
+                if (g >= (long long)base && g + 2 <= (long long)end) {
                     const unsigned int l = (unsigned int)(g - base);
                     unsigned long long a = s64[l], b = s64[l + 1];
                     int4 v;
@@ -494,7 +495,7 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
                 } else {
 #pragma unroll
                     for (int i = 0; i < 2; i++)
-                        if (g + i >= base && g + i < end) st_stream_8(dst + g + i, (long long)s64[(unsigned int)(g + i - base)]);
+                        if (g + i >= (long long)base && g + i < (long long)end) st_stream_8(dst + g + i, (long long)s64[(unsigned int)(g + i - (long long)base)]);
                 }
             }
         }

@@ -396,3 +396,27 @@ def test_agg_smem_path_adapts_to_high_cardinality(gu):
     exp = orc.hash_agg(cols, [], aggs, 16)
     got = gu.gpu_hash_agg(cols, [], aggs, 16, mem="device", batches=2)
     gu.approx_rows_equal(got, exp, float_cols=[1, 5], key_cols=[], rtol=RTOL)
+
+
+def test_fast_join_unaligned_output_columns(gu):
+    """Caller-owned device output columns that are only naturally aligned (views at odd offsets): the aligned flush
+    must adapt to the address, not assume a 16-byte-aligned base."""
+    import torch
+    from galaxysql_b200 import api, native as N
+    outer, inner, kc = _unique_key_tables(30_000, 70_000, 45_000, np.int64, 2, 2, seed=4242)
+    j = api.HashJoin(gu.ctx(), N.JOIN_INNER, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    j.build_consume(inner)
+    j.build_finish()
+    assert j.info().fast_path == 1
+    n = len(outer[0][0])
+    tt = {N.T_INT32: torch.int32, N.T_INT64: torch.int64, N.T_FP64: torch.float64}
+    outs = []
+    for q, t in enumerate(j.out_types):
+        base = torch.zeros(n + 8, dtype=tt[t], device="cuda")
+        outs.append((base[(q % 3) + 1:], None))
+    rows = j.probe_into(gu.to_device(outer), outs, n)
+    gu.ctx().sync()
+    got = [(c[:rows].cpu().numpy(), None) for c, _ in outs]
+    spec = orc.JoinSpec(orc.JOIN_INNER, [kc], [0], [orc.T_INT64])
+    assert ku.rows_multiset(got) == ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    j.close()
