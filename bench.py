@@ -209,21 +209,17 @@ def run_ours(args):
         if rank == 0:
             uid.copy_(torch.tensor(list(api.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
-        ctx_x = api.Context(local_rank)  # exchange context: own stream + communicator
-        api.comm_init(ctx_x, world, rank, bytes(uid.cpu().tolist()))
-        xb = api.Exchange(ctx_x, types, [0], world)
-        xp = api.Exchange(ctx_x, types, [0], world)
+        api.comm_init(ctx, world, rank, bytes(uid.cpu().tolist()))
+        xb = api.Exchange(ctx, types, [0], world)
+        xp = api.Exchange(ctx, types, [0], world)
         bcap = int(nb * 1.05) + 1_000_000
-        scap = int((npr + 3) // 4 * 1.05) + 1_000_000
         rb = [(torch.empty(bcap, dtype=tt[t], device=dev), None) for t in types]
-        rp = [[(torch.empty(scap, dtype=tt[t], device=dev), None) for t in types] for _ in range(2)]
+        rp = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in types]
 
     def b(cols):
         return [(c, None) for c in cols]
 
     state = {"out_rows": 0, "info": None}
-
-    NSLAB = 4  # N > 1: the probe side is exchanged in slabs so that slab i+1 travels while slab i is being probed
 
     def step_single():
         j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nb)
@@ -234,52 +230,15 @@ def run_ours(args):
         j.close()
 
     def step_multi():
-        import queue
-        import threading
-        ready, free = queue.Queue(), queue.Queue()
-        for i in range(2):
-            free.put(i)
-        slab = (npr + NSLAB - 1) // NSLAB
-        err = []
-
-        def exchanger():  # its own context / stream / NCCL communicator: the AllToAllv overlaps the join kernels
-            try:
-                torch.cuda.set_device(local_rank)
-                nbr, _ = xb.all_to_all_into(b(build), rb, bcap)
-                ctx_x.sync()
-                ready.put(("build", nbr, None))
-                for s_ in range(NSLAB):
-                    lo, hi = s_ * slab, min(npr, (s_ + 1) * slab)
-                    buf = free.get()
-                    n_, _ = xp.all_to_all_into([(c[lo:hi], None) for c in probe], rp[buf], scap)
-                    ctx_x.sync()
-                    ready.put(("probe", n_, buf))
-                ready.put(("done", 0, None))
-            except Exception as e:  # surface in the main thread
-                err.append(e)
-                ready.put(("done", 0, None))
-
-        th = threading.Thread(target=exchanger)
-        th.start()
-        kind, nbr, _ = ready.get()
-        if kind != "build":
-            th.join()
-            raise err[0]
+        # exchange both sides on the join key, then join locally.  (A slabbed variant that overlapped the AllToAllv of
+        # slab i+1 with the probe of slab i through a second context + host thread measured SLOWER in r01 — 125 ms vs
+        # 103 ms per step at N = 2 — so the step stays sequential.)
+        nbr, _ = xb.all_to_all_into(b(build), rb, bcap)
+        npr_r, _ = xp.all_to_all_into(b(probe), rp, cap)
         j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nbr)
         j.build_consume([(c[:nbr], None) for c, _ in rb])
         j.build_finish()
-        total = 0
-        while True:
-            kind, n_, buf = ready.get()
-            if kind == "done":
-                break
-            outs = [(c[total:], None) for c, _ in out_cols]
-            total += j.probe_into([(c[:n_], None) for c, _ in rp[buf]], outs, cap - total)
-            free.put(buf)
-        th.join()
-        if err:
-            raise err[0]
-        state["out_rows"] = total
+        state["out_rows"] = j.probe_into([(c[:npr_r], None) for c, _ in rp], out_cols, cap)
         state["info"] = j.info()
         j.close()
 
@@ -296,10 +255,7 @@ def run_ours(args):
     ctx.profile(True)
     ctx.profile_reset()
     launches0 = ctx.launch_count
-    if world > 1:
-        ctx_x.profile(True)
-        ctx_x.profile_reset()
-        launches0 += ctx_x.launch_count
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -317,10 +273,7 @@ def run_ours(args):
     prof = ctx.profile_dump()
     ctx.profile(False)
     launches = ctx.launch_count - launches0
-    if world > 1:
-        prof.update(ctx_x.profile_dump())
-        ctx_x.profile(False)
-        launches += ctx_x.launch_count
+
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -385,7 +338,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        ctx_x.lib.gsql_comm_destroy(ctx_x.ptr)
+        ctx.lib.gsql_comm_destroy(ctx.ptr)
         dist.destroy_process_group()
 
 
