@@ -14,6 +14,7 @@
 // NCCL is bound at run time (dlopen) so that the library shares the process's NCCL with torch.distributed.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 
 #include <cub/device/device_scan.cuh>
 
@@ -87,6 +88,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t *, ncclConfig_t *) = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -111,6 +113,7 @@ NcclApi *nccl_api() {
     BIND(GetUniqueId, "ncclGetUniqueId");
     BIND(CommInitRank, "ncclCommInitRank");
     BIND(CommDestroy, "ncclCommDestroy");
+    BIND(CommSplit, "ncclCommSplit");
     BIND(AllGather, "ncclAllGather");
     BIND(Send, "ncclSend");
     BIND(Recv, "ncclRecv");
@@ -294,6 +297,20 @@ extern "C" gsql_status gsql_comm_init(gsql_ctx *ctx, int32_t nranks, int32_t ran
     ctx->nccl_comm = comm;
     ctx->nranks = nranks;
     ctx->rank = rank;
+    // stripe communicators
+    int want = 3;
+    if (const char *e = getenv("GSQL_XCHG_STRIPES")) want = atoi(e) - 1;
+    if (want > 7) want = 7;
+    ctx->n_extra = 0;
+    if (nranks > 1 && api->CommSplit) {
+        for (int i = 0; i < want; i++) {
+            ncclComm_t extra = nullptr;
+            if (api->CommSplit(comm, 0, rank, &extra, nullptr) != ncclSuccess || !extra) break;
+            ctx->nccl_extra[i] = extra;
+            cudaStreamCreateWithFlags(&ctx->xstreams[i], cudaStreamNonBlocking);
+            ctx->n_extra = i + 1;
+        }
+    }
     return GSQL_OK;
 }
 
@@ -301,6 +318,13 @@ extern "C" gsql_status gsql_comm_destroy(gsql_ctx *ctx) {
     if (!ctx) return GSQL_E_INVALID;
     if (ctx->nccl_comm) {
         cudaStreamSynchronize(ctx->stream);
+        for (int i = 0; i < ctx->n_extra; i++) {
+            cudaStreamSynchronize(ctx->xstreams[i]);
+            nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_extra[i]);
+            cudaStreamDestroy(ctx->xstreams[i]);
+            ctx->nccl_extra[i] = nullptr;
+        }
+        ctx->n_extra = 0;
         nccl_api()->CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
     }
@@ -368,23 +392,43 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     // whole matrix, so all of them learn whether anyone overflows... each rank has its own capacity, so the caller
     // contract is: size `out` for the worst case (sum over sources) or retry collectively.
     if (total > out_capacity) return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
-    // ---- 3. AllToAllv: one grouped send/recv per column (and per null mask)
+    // ---- 3. AllToAllv: grouped send/recv per column (and per null mask), striped over 1 + n_extra communicators /
+    //         streams so that several NCCL p2p kernels run side by side
     {
         KernelScope ks(ctx, "xchg_alltoall");
-        GSQL_NCCL(ctx, api->GroupStart());
-        for (int c = 0; c < s.n_cols; c++) {
-            size_t w = (size_t)gsql_type_width(s.types[c]);
-            for (int peer = 0; peer < R; peer++) {
-                int64_t ns = send_counts[(size_t)peer], nr = matrix[(size_t)peer * R + ctx->rank];
-                if (ns > 0) GSQL_NCCL(ctx, api->Send((char *)sdata[c].p + (size_t)soff[(size_t)peer] * w, (size_t)ns * w, ncclInt8, peer, comm, ctx->stream));
-                if (nr > 0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].data + (size_t)roff[(size_t)peer] * w, (size_t)nr * w, ncclInt8, peer, comm, ctx->stream));
-                if (out->cols[c].nulls) {
-                    if (ns > 0) GSQL_NCCL(ctx, api->Send((char *)snull[c].p + soff[(size_t)peer], (size_t)ns, ncclInt8, peer, comm, ctx->stream));
-                    if (nr > 0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].nulls + roff[(size_t)peer], (size_t)nr, ncclInt8, peer, comm, ctx->stream));
+        const int K = 1 + ctx->n_extra;
+        cudaEvent_t ready;
+        GSQL_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        GSQL_CUDA(ctx, cudaEventRecord(ready, ctx->stream));  // the partitioned send buffers are complete
+        for (int k = 0; k < K; k++) {
+            ncclComm_t cm = k == 0 ? comm : (ncclComm_t)ctx->nccl_extra[k - 1];
+            cudaStream_t st = k == 0 ? ctx->stream : ctx->xstreams[k - 1];
+            if (k > 0) GSQL_CUDA(ctx, cudaStreamWaitEvent(st, ready, 0));
+            GSQL_NCCL(ctx, api->GroupStart());
+            for (int c = 0; c < s.n_cols; c++) {
+                size_t w = (size_t)gsql_type_width(s.types[c]);
+                for (int peer = 0; peer < R; peer++) {
+                    int64_t ns = send_counts[(size_t)peer], nr = matrix[(size_t)peer * R + ctx->rank];
+                    // stripe k carries rows [n*k/K, n*(k+1)/K) of every segment
+                    int64_t s0 = ns * k / K, s1 = ns * (k + 1) / K, r0 = nr * k / K, r1 = nr * (k + 1) / K;
+                    if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)sdata[c].p + (size_t)(soff[(size_t)peer] + s0) * w, (size_t)(s1 - s0) * w, ncclInt8, peer, cm, st));
+                    if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].data + (size_t)(roff[(size_t)peer] + r0) * w, (size_t)(r1 - r0) * w, ncclInt8, peer, cm, st));
+                    if (out->cols[c].nulls) {
+                        if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)snull[c].p + soff[(size_t)peer] + s0, (size_t)(s1 - s0), ncclInt8, peer, cm, st));
+                        if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].nulls + roff[(size_t)peer] + r0, (size_t)(r1 - r0), ncclInt8, peer, cm, st));
+                    }
                 }
             }
+            GSQL_NCCL(ctx, api->GroupEnd());
         }
-        GSQL_NCCL(ctx, api->GroupEnd());
+        for (int k = 1; k < K; k++) {  // join the stripes back into the context stream
+            cudaEvent_t done;
+            GSQL_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            GSQL_CUDA(ctx, cudaEventRecord(done, ctx->xstreams[k - 1]));
+            GSQL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done, 0));
+            GSQL_CUDA(ctx, cudaEventDestroy(done));
+        }
+        GSQL_CUDA(ctx, cudaEventDestroy(ready));
     }
     out->rows = total;
     return GSQL_OK;
