@@ -299,7 +299,11 @@ def run_ours(args):
     probe_rows_rank = n_out
     peak, peak_src = measured_peak_gbs()
     achieved = PROBE_ALG_BYTES * probe_rows_rank / (probe_ms / 1000.0) / 1e9 if probe_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fj_probe launch over 1 B probe rows (unpartitioned default),
+    # from the `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (prof_r01h): 141.97 + 31.98 GB.  Every
+    # random 16-byte table read costs a ~128-byte HBM fetch on this part, so traffic is ~2.6x the algorithmic bytes.
+    traffic = 173.95e9 * (probe_rows_rank / 1e9) if state["info"].partitions == 1 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "+".join(sorted(probe_kernels)), "kernel_ms_per_step": probe_ms,
                 "algorithmic_bytes_per_probe_row": PROBE_ALG_BYTES, "peak_source": peak_src,
                 "per_kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items())}}
