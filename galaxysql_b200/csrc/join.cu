@@ -498,12 +498,22 @@ static void fill_build_cols(gsql_join *j, DColSet *build, KeySet *bkeys) {
     default: { constexpr int WW = 4; __VA_ARGS__; } break; \
     }
 
+static int64_t env_i64(const char *name, int64_t dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoll(v) : dflt;
+}
+
+// input double-buffering (cp.async) when the three tile buffers still leave room for 2 blocks per SM
+static bool fj_scatter_pipe(int W, int P) {
+    return env_i64("GSQL_JOIN_SCATTER_PIPE", 1) && fj::scatter_smem_bytes(W, P, true) + 4096 <= 112 * 1024;
+}
+
 static fj::PartGeom fj_geom(gsql_ctx *ctx, int64_t rows, int P, int W) {
     fj::PartGeom g;
     g.rows = rows;
     g.P = P;
-    size_t smem = fj::scatter_smem_bytes(W, P) + 4096;
-    int per_sm = (int)(200 * 1024 / smem);
+    size_t smem = fj::scatter_smem_bytes(W, P, fj_scatter_pipe(W, P)) + 2048;  // + static shared memory and the 1 KB per-block reserve
+    int per_sm = (int)(227 * 1024 / smem);
     if (per_sm > 2) per_sm = 2;  // 512-thread CTAs, <= 64 registers: two per SM
     if (per_sm < 1) per_sm = 1;
     int64_t nblocks = (int64_t)ctx->sm_count * per_sm;
@@ -518,7 +528,7 @@ static fj::PartGeom fj_geom(gsql_ctx *ctx, int64_t rows, int P, int W) {
 
 // Packs `rows` rows of `cols` into partition order: out[rows * W] words.
 static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::Layout &L, int64_t rows, int P, unsigned long long *out,
-                                int32_t *flags, const char *tag) {
+                                int32_t *flags, const char *tag, DevBuf *keep_offs = nullptr, int *hist_blocks = nullptr) {
     const int W = L.nwords;
     fj::PartGeom g = fj_geom(ctx, rows, P, W);
     int64_t nh = (int64_t)P * g.nblocks;
@@ -540,26 +550,37 @@ static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::La
         KernelScope ks(ctx, name.c_str());
         GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist.as<int64_t>(), offs.as<int64_t>(), nh + 1, ctx->stream));
     }
-    size_t smem = fj::scatter_smem_bytes(W, P);
+    const bool pipe = fj_scatter_pipe(W, P);
+    size_t smem = fj::scatter_smem_bytes(W, P, pipe);
     name = std::string("join_fast_scatter_") + tag;
     {
         KernelScope ks(ctx, name.c_str());
         FJ_DISPATCH_W(W, {
-            static int attr_smem = 0;
-            if ((int)smem > attr_smem) {
-                GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                attr_smem = (int)smem;
+            if (pipe) {
+                static int attr_smem = 0;
+                if ((int)smem > attr_smem) {
+                    GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_smem = (int)smem;
+                }
+                fj::k_fj_scatter<WW, true><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
+            } else {
+                static int attr_smem = 0;
+                if ((int)smem > attr_smem) {
+                    GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    attr_smem = (int)smem;
+                }
+                fj::k_fj_scatter<WW, false><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
             }
-            fj::k_fj_scatter<WW><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
         });
     }
     GSQL_CUDA(ctx, cudaGetLastError());
+    if (keep_offs) {  // offs[p * nblocks] = first packed row of partition p; offs[P * nblocks] = rows
+        keep_offs->release();
+        keep_offs->p = offs.p; keep_offs->bytes = offs.bytes; keep_offs->ctx = offs.ctx;
+        offs.p = nullptr; offs.bytes = 0;
+    }
+    if (hist_blocks) *hist_blocks = g.nblocks;
     return GSQL_OK;
-}
-
-static int64_t env_i64(const char *name, int64_t dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoll(v) : dflt;
 }
 
 // Decides eligibility, builds the packed-row table; leaves j->fast.enabled = false when the generic path must run.
@@ -580,17 +601,21 @@ static gsql_status fast_build(gsql_join *j) {
     if (!fj::make_layout(j->build_types, j->n_build, j->bkey_cols[0], &F.bl)) return GSQL_OK;
     if (!fj::make_layout(j->probe_types, j->n_probe, j->pkey_cols[0], &F.pl)) return GSQL_OK;
     F.eligible = true;
-    // Default: one partition (probe straight from the input columns).  The radix-partitioned L2-resident mode
-    // (GSQL_JOIN_PART_BYTES=16777216) has the higher ceiling but its scatter pass still costs more than it saves (r01:
-    // 38.9 ms vs 37.0 ms per C2 step — DESIGN.md §Kernels).
-    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 1ll << 40);
+    // A table that fits in L2 next to the streams (<= GSQL_JOIN_L2_TABLE_BYTES, 64 MB) is probed straight from the input
+    // columns.  A larger one is radix-partitioned on the key hash into slices of GSQL_JOIN_PART_BYTES (16 MB): both
+    // sides are packed into partition order, so every table access of the insert and of the probe hits a slice that
+    // is resident in L2 — an unpartitioned probe pays a ~128-byte HBM fetch for each random 16-byte slot read
+    // (profiles/r01_ncu_summary.md, prof_r01h: 174 GB moved for 1 B probe rows vs 88 GB here).
+    F.part_bytes = env_i64("GSQL_JOIN_PART_BYTES", 16ll << 20);
     if (F.part_bytes < 4096) F.part_bytes = 4096;
     F.sub_batch = env_i64("GSQL_JOIN_SUB_BATCH", 1ll << 30);
     if (F.sub_batch < fj::TILE) F.sub_batch = fj::TILE;
+    F.part_min_rows = env_i64("GSQL_JOIN_PART_MIN_ROWS", 1ll << 20);
     const int BW = F.bl.nwords;
     int64_t want = j->build_rows * env_i64("GSQL_JOIN_SLOTS_PER_ROW", 3);  // load factor 1/3: short probe sequences
     if (want < 1024) want = 1024;
     int64_t P = div_up(want * BW * 8, F.part_bytes);
+    if (!getenv("GSQL_JOIN_PART_BYTES") && want * BW * 8 <= env_i64("GSQL_JOIN_L2_TABLE_BYTES", 64ll << 20)) P = 1;
     if (P > fj::MAX_P) P = fj::MAX_P;
     if (P < 1) P = 1;
     int64_t spp = div_up(want, P);
@@ -600,22 +625,48 @@ static gsql_status fast_build(gsql_join *j) {
     GSQL_TRY(F.flags.alloc(ctx, fj::FL_COUNT * 4));
     GSQL_TRY(F.cursor.alloc(ctx, 16));
     GSQL_CUDA(ctx, cudaMemsetAsync(F.flags.p, 0, fj::FL_COUNT * 4, ctx->stream));
-    {
+    DColSet build;
+    KeySet bkeys;
+    fill_build_cols(j, &build, &bkeys);
+    DevBuf packed, part_offs;
+    const bool fused = F.P > 1 && env_i64("GSQL_JOIN_BUILD_FUSED", 1);
+    if (!fused) {
         KernelScope ks(ctx, "join_fast_table_init");
         int grid = grid_rows(ctx, (int64_t)F.nslots, 256, 8);
         FJ_DISPATCH_W(BW, { fj::k_fj_table_init<WW><<<grid, 256, 0, ctx->stream>>>(F.table.as<unsigned long long>(), F.nslots); });
     }
-    DColSet build;
-    KeySet bkeys;
-    fill_build_cols(j, &build, &bkeys);
-    DevBuf packed;
     const unsigned long long *src = nullptr;
+    int hist_blocks = 0;
     if (F.P > 1) {
         GSQL_TRY(packed.alloc(ctx, (size_t)j->build_rows * BW * 8));
-        GSQL_TRY(fj_partition(ctx, build, F.bl, j->build_rows, F.P, packed.as<unsigned long long>(), F.flags.as<int32_t>(), "build"));
+        GSQL_TRY(fj_partition(ctx, build, F.bl, j->build_rows, F.P, packed.as<unsigned long long>(), F.flags.as<int32_t>(), "build",
+                              fused ? &part_offs : nullptr, &hist_blocks));
         src = packed.as<unsigned long long>();
     }
-    {
+    if (fused) {
+        // groups of partitions of ~16 MB (three groups are dirty in L2 at a time; 32 MB measured 35 % slower), never smaller than 2 * MAX_DISP slots
+        int64_t gbytes = env_i64("GSQL_JOIN_BUILD_GROUP_BYTES", 16ll << 20);
+        int64_t slice = (int64_t)spp * BW * 8;
+        int G = (int)(gbytes / slice > 1 ? gbytes / slice : 1);
+        while ((int64_t)G * spp < 2 * fj::MAX_DISP) G++;
+        if (G > F.P) G = F.P;
+        KernelScope ks(ctx, "join_fast_build_part");
+        FJ_DISPATCH_W(BW, {
+            int per_sm = 0;
+            GSQL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fj::k_fj_build_part<WW>, fj::THREADS, 0));
+            if (per_sm < 1) return gsql_set_error(ctx, GSQL_E_CUDA, "k_fj_build_part cannot be made resident");
+            if (per_sm > 2) per_sm = 2;
+            int grid = ctx->sm_count * per_sm;
+            const unsigned long long *a_packed = src;
+            const int64_t *a_offs = part_offs.as<int64_t>();
+            int a_nb = hist_blocks, a_P = F.P, a_G = G;
+            unsigned long long *a_table = F.table.as<unsigned long long>();
+            uint64_t a_nslots = F.nslots, a_spp = (uint64_t)spp;
+            int32_t *a_flags = F.flags.as<int32_t>();
+            void *args[] = {&a_packed, &a_offs, &a_nb, &a_P, &a_G, &a_table, &a_nslots, &a_spp, &a_flags};
+            GSQL_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)fj::k_fj_build_part<WW>, dim3(grid), dim3(fj::THREADS), args, 0, ctx->stream));
+        });
+    } else {
         KernelScope ks(ctx, "join_fast_insert");
         int64_t itiles = div_up(j->build_rows, fj::TILE);
         int grid = (int)(itiles < (int64_t)ctx->sm_count * 2 ? itiles : (int64_t)ctx->sm_count * 2);
@@ -893,7 +944,8 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
     gsql_ctx *ctx = j->ctx;
     const int PW = F.pl.nwords, BW = F.bl.nwords;
     const unsigned long long *src = nullptr;
-    if (F.P > 1) {
+    // a batch too small to amortise the two partitioning passes probes the (same) table directly
+    if (F.P > 1 && m >= F.part_min_rows) {
         GSQL_TRY(fj_partition(ctx, cols, F.pl, m, F.P, packed, F.flags.as<int32_t>(), "probe"));
         src = packed;
     }

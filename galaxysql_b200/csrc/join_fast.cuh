@@ -19,6 +19,7 @@
 // with unique build keys and no NULLs (row multiset identical; output order is unspecified in both).
 #pragma once
 
+#include <cooperative_groups.h>
 #include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -192,6 +193,11 @@ __device__ __forceinline__ unsigned long long load_key(const DCol &col, int64_t 
     return (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
 }
 
+// Partition of a key hash.  Only the high 32 bits take part (one IMAD.HI): the result may differ from
+// slot / slots_per_partition for a vanishing fraction of keys, which costs those rows an access outside the resident
+// slice, never correctness (slots are always addressed globally).
+__device__ __forceinline__ unsigned int part_of(uint64_t h, int P) { return __umulhi((unsigned int)(h >> 32), (unsigned int)P); }
+
 struct PartGeom {
     int64_t rows, chunk;  // rows per block (multiple of TILE)
     int32_t P, nblocks;
@@ -217,7 +223,7 @@ __global__ void __launch_bounds__(THREADS) k_fj_hist(DCol keycol, PartGeom g, in
             int64_t r = t0 + k * THREADS + threadIdx.x;
             if (r < r1) {
                 sentinel |= key[k] == KEY_EMPTY;
-                atomicAdd(&sh_hist[(unsigned)__umul64hi(key_hash(key[k]), (uint64_t)g.P)], 1u);
+                atomicAdd(&sh_hist[part_of(key_hash(key[k]), g.P)], 1u);
             }
         }
     }
@@ -226,16 +232,100 @@ __global__ void __launch_bounds__(THREADS) k_fj_hist(DCol keycol, PartGeom g, in
     for (int i = threadIdx.x; i < g.P; i += THREADS) hist[(int64_t)i * g.nblocks + blockIdx.x] = sh_hist[i];
 }
 
-// ---- pass 2: pack rows and scatter them into partition order through a shared-memory staged tile
-template <int W>
+// ---- cp.async (LDGSTS) helpers: per-thread asynchronous global -> shared copies, grouped and waited per tile
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Issues the asynchronous loads of one tile: column c lands at buf + (bytes of columns < c) * TILE, element
+// (k*THREADS + tid); every thread later reads back exactly the elements it issued (no block barrier needed).
+// FULL tiles carry no per-row bounds checks; all per-row addresses are (per-column base) + compile-time offsets.
+template <bool FULL>
+__device__ __forceinline__ void tile_prefetch(const DColSet &cols, const Layout &L, int64_t t0, int n_tile, unsigned char *buf) {
+    const unsigned tid = threadIdx.x;
+    unsigned char *sp = buf + tid * 4u;
+#pragma unroll 1
+    for (int c = 0; c < L.ncols; c++) {
+        const DCol &col = cols.c[c];
+        if (col.type == GSQL_T_INT32) {
+            const int *gp = reinterpret_cast<const int *>(col.data) + t0 + tid;
+#pragma unroll
+            for (int k = 0; k < RPT; k++)
+                if (FULL || (int)(k * THREADS + tid) < n_tile) cp_async_4(sp + k * THREADS * 4, gp + k * THREADS);
+            sp += TILE * 4;
+        } else {
+            const long long *gp = reinterpret_cast<const long long *>(col.data) + t0 + tid;
+            unsigned char *sp8 = sp + tid * 4u;
+#pragma unroll
+            for (int k = 0; k < RPT; k++)
+                if (FULL || (int)(k * THREADS + tid) < n_tile) cp_async_8(sp8 + k * THREADS * 8, gp + k * THREADS);
+            sp += TILE * 8;
+        }
+    }
+    cp_async_commit();
+}
+
+template <int W, bool FULL>
+__device__ __forceinline__ void pack_tile_smem(const DColSet &cols, const Layout &L, int n_tile, const unsigned char *buf,
+                                               unsigned long long (&w)[RPT][W]) {
+#pragma unroll
+    for (int k = 0; k < RPT; k++)
+#pragma unroll
+        for (int i = 0; i < W; i++) w[k][i] = 0;
+    const unsigned tid = threadIdx.x;
+    const unsigned char *sp = buf + tid * 4u;
+#pragma unroll 1
+    for (int c = 0; c < L.ncols; c++) {
+        const bool is32 = cols.c[c].type == GSQL_T_INT32, iskey = c == L.key_col;
+        const int wi = L.word[c];
+        const int sh = L.half[c] == 1 ? 32 : 0;
+        unsigned long long v[RPT];
+        if (is32) {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                int x = (FULL || (int)(k * THREADS + tid) < n_tile) ? *reinterpret_cast<const int *>(sp + k * THREADS * 4) : 0;
+                v[k] = iskey ? (unsigned long long)(long long)x : (unsigned long long)(unsigned)x;
+            }
+            sp += TILE * 4;
+        } else {
+            const unsigned char *sp8 = sp + tid * 4u;
+#pragma unroll
+            for (int k = 0; k < RPT; k++)
+                v[k] = (FULL || (int)(k * THREADS + tid) < n_tile) ? *reinterpret_cast<const unsigned long long *>(sp8 + k * THREADS * 8) : 0ULL;
+            sp += TILE * 8;
+        }
+#pragma unroll
+        for (int i = 0; i < W; i++)
+            if (i == wi) {
+#pragma unroll
+                for (int k = 0; k < RPT; k++) w[k][i] |= v[k] << sh;
+            }
+    }
+}
+
+// ---- pass 2: pack rows and scatter them into partition order through a shared-memory staged tile.  PIPE: the
+// column loads of tile t+1 are issued (cp.async into a second input buffer) before tile t is ranked, staged and
+// flushed, so the HBM latency of the loads overlaps the shared-memory work of the previous tile.
+template <int W, bool PIPE>
 __global__ void __launch_bounds__(THREADS, 2) k_fj_scatter(const __grid_constant__ DColSet cols, const __grid_constant__ Layout L, PartGeom g,
                                                         const int64_t *__restrict__ offs, unsigned long long *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem_raw);           // TILE * W
     unsigned long long *cur = stage + (size_t)TILE * W;                                      // P
-    unsigned int *hist = reinterpret_cast<unsigned int *>(cur + g.P);                        // P
+    unsigned long long *delta = cur + g.P;                                                   // P
+    unsigned int *hist = reinterpret_cast<unsigned int *>(delta + g.P);                      // P
     unsigned int *start = hist + g.P;                                                        // P
     unsigned short *spid = reinterpret_cast<unsigned short *>(start + g.P);                  // TILE
+    unsigned char *inbuf = reinterpret_cast<unsigned char *>(spid + TILE);                   // PIPE: 2 * TILE * W * 8
     typedef cub::BlockScan<unsigned int, THREADS> BlockScan;
     __shared__ typename BlockScan::TempStorage scan_tmp;
 
@@ -246,21 +336,47 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_scatter(const __grid_constant
     __syncthreads();
     int64_t r0 = (int64_t)blockIdx.x * g.chunk;
     int64_t r1 = r0 + g.chunk < g.rows ? r0 + g.chunk : g.rows;
-    for (int64_t t0 = r0; t0 < r1; t0 += TILE) {
+    if (PIPE && r0 < r1) {
+        if (r1 - r0 >= TILE) tile_prefetch<true>(cols, L, r0, TILE, inbuf);
+        else tile_prefetch<false>(cols, L, r0, (int)(r1 - r0), inbuf);
+    }
+    int it = 0;
+    for (int64_t t0 = r0; t0 < r1; t0 += TILE, it++) {
         unsigned long long w[RPT][W];
         unsigned int pid[RPT], rank[RPT];
-        pack_tile<W>(cols, L, t0 + threadIdx.x, r1, w);
+        const int n_tile = (int)(r1 - t0 < TILE ? r1 - t0 : TILE);
+        const bool full = n_tile == TILE;
+        if (PIPE) {
+            const int64_t left = r1 - (t0 + TILE);
+            unsigned char *nbuf = inbuf + (size_t)((it + 1) & 1) * TILE * W * 8;
+            if (left >= TILE) tile_prefetch<true>(cols, L, t0 + TILE, TILE, nbuf);
+            else if (left > 0) tile_prefetch<false>(cols, L, t0 + TILE, (int)left, nbuf);
+            else cp_async_commit();
+            cp_async_wait<1>();
+            const unsigned char *cbuf = inbuf + (size_t)(it & 1) * TILE * W * 8;
+            if (full) pack_tile_smem<W, true>(cols, L, n_tile, cbuf, w);
+            else pack_tile_smem<W, false>(cols, L, n_tile, cbuf, w);
+        } else {
+            pack_tile<W>(cols, L, t0 + threadIdx.x, r1, w);
+        }
+        if (full) {
 #pragma unroll
-        for (int k = 0; k < RPT; k++) {
-            int64_t r = t0 + k * THREADS + threadIdx.x;
-            pid[k] = 0xffffffffu;
-            if (r < r1) {
-                pid[k] = (unsigned)__umul64hi(key_hash(w[k][0]), (uint64_t)g.P);
+            for (int k = 0; k < RPT; k++) {
+                pid[k] = part_of(key_hash(w[k][0]), g.P);
                 rank[k] = atomicAdd(&hist[pid[k]], 1u);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < RPT; k++) {
+                pid[k] = 0xffffffffu;
+                if ((int)(k * THREADS + threadIdx.x) < n_tile) {
+                    pid[k] = part_of(key_hash(w[k][0]), g.P);
+                    rank[k] = atomicAdd(&hist[pid[k]], 1u);
+                }
             }
         }
         __syncthreads();
-        {  // exclusive scan of hist[0..P) -> start[]
+        {  // exclusive scan of hist[0..P) -> start[]; delta[p] = (global cursor of p) - start[p]
             constexpr int IPT = MAX_P / THREADS;
             unsigned int v[IPT];
 #pragma unroll
@@ -272,41 +388,53 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_scatter(const __grid_constant
 #pragma unroll
             for (int i = 0; i < IPT; i++) {
                 int p = threadIdx.x * IPT + i;
-                if (p < g.P) start[p] = v[i];
+                if (p < g.P) {
+                    start[p] = v[i];
+                    unsigned long long c = cur[p];
+                    delta[p] = c - v[i];
+                    cur[p] = c + hist[p];
+                    hist[p] = 0;
+                }
             }
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < RPT; k++) {
-            if (pid[k] != 0xffffffffu) {
+            if (full || pid[k] != 0xffffffffu) {
                 unsigned int pos = start[pid[k]] + rank[k];
+                if (W == 2) {
+                    int4 v;
+                    v.x = (int)(unsigned)w[k][0]; v.y = (int)(unsigned)(w[k][0] >> 32);
+                    v.z = (int)(unsigned)w[k][W - 1]; v.w = (int)(unsigned)(w[k][W - 1] >> 32);
+                    *reinterpret_cast<int4 *>(stage + (size_t)pos * 2) = v;
+                } else {
 #pragma unroll
-                for (int i = 0; i < W; i++) stage[(size_t)pos * W + i] = w[k][i];
+                    for (int i = 0; i < W; i++) stage[(size_t)pos * W + i] = w[k][i];
+                }
                 spid[pos] = (unsigned short)pid[k];
             }
         }
         __syncthreads();
-        int n_tile = (int)(r1 - t0 < TILE ? r1 - t0 : TILE);
-        for (int i = threadIdx.x; i < n_tile; i += THREADS) {  // consecutive threads -> consecutive addresses of a run
-            unsigned int p = spid[i];
-            unsigned long long dst = cur[p] + (unsigned)(i - start[p]);
-            if (W == 2) {
-                st_stream_16(out + dst * 2, *reinterpret_cast<const int4 *>(stage + (size_t)i * 2));
-            } else {
 #pragma unroll
-                for (int j = 0; j < W; j++) st_stream_8(out + dst * W + j, (long long)stage[(size_t)i * W + j]);
+        for (int k = 0; k < RPT; k++) {  // consecutive threads -> consecutive addresses of a run
+            const int i = k * THREADS + threadIdx.x;
+            if (full || i < n_tile) {
+                unsigned long long dst = delta[spid[i]] + (unsigned)i;
+                if (W == 2) {
+                    st_stream_16(out + dst * 2, *reinterpret_cast<const int4 *>(stage + (size_t)i * 2));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < W; j++) st_stream_8(out + dst * W + j, (long long)stage[(size_t)i * W + j]);
+                }
             }
         }
-        __syncthreads();
-        for (int p = threadIdx.x; p < g.P; p += THREADS) {
-            cur[p] += hist[p];
-            hist[p] = 0;
-        }
-        __syncthreads();
+        __syncthreads();  // stage / spid / delta are rewritten by the next tile
     }
 }
 
-static size_t scatter_smem_bytes(int W, int P) { return (size_t)TILE * W * 8 + (size_t)P * 8 + (size_t)P * 4 * 2 + (size_t)TILE * 2; }
+static size_t scatter_smem_bytes(int W, int P, bool pipe) {
+    return (size_t)TILE * W * 8 + (size_t)P * 8 * 2 + (size_t)P * 4 * 2 + (size_t)TILE * 2 + (pipe ? (size_t)2 * TILE * W * 8 : 0);
+}
 
 // ---- table
 template <int W>
@@ -371,6 +499,81 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_insert(const unsigned long lo
                 any |= pending[k];
             }
             if (++disp > MAX_DISP) { if (any) flags[FL_DISP] = 1; break; }
+        }
+    }
+}
+
+// ---- partitioned build: table initialisation fused with the inserts, one partition GROUP at a time (cooperative
+// launch, one grid barrier per group).  A group's slice (~32 MB) is written EMPTY and then receives its CAS inserts
+// while it is still dirty in L2, so the table crosses HBM once (the final write-back) instead of three times (init
+// write-back, fetch on the first atomic, write-back again) — atomics on L2-resident lines run ~9x faster than on
+// lines that miss (profiles/r01_microbench.txt).  Group g+1 is initialised BEFORE the barrier that precedes the
+// inserts of group g, so linear probing that runs past the end of group g (bounded by MAX_DISP <= group size) only
+// ever meets initialised slots.
+template <int W>
+__global__ void __launch_bounds__(THREADS, 2) k_fj_build_part(const unsigned long long *__restrict__ packed, const int64_t *__restrict__ offs,
+                                                           int nblocks_hist, int P, int G, unsigned long long *table, uint64_t nslots, uint64_t spp,
+                                                           int32_t *flags) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int ngroups = (P + G - 1) / G;
+    const uint64_t gstride = (uint64_t)gridDim.x * THREADS, gtid = (uint64_t)blockIdx.x * THREADS + threadIdx.x;
+    auto init_group = [&](int g) {
+        if (g >= ngroups) return;
+        const uint64_t s0 = (uint64_t)g * G * spp;
+        uint64_t s1 = s0 + (uint64_t)G * spp;
+        if (s1 > nslots) s1 = nslots;
+        for (uint64_t i = s0 + gtid; i < s1; i += gstride) {
+            if (W == 2) {
+                int4 v;
+                v.x = 0; v.y = (int)0x80000000u; v.z = 0; v.w = 0;  // { KEY_EMPTY, 0 }
+                *reinterpret_cast<int4 *>(table + i * 2) = v;
+            } else {
+                table[i * W] = KEY_EMPTY;
+#pragma unroll
+                for (int j = 1; j < W; j++) table[i * W + j] = 0;
+            }
+        }
+    };
+    init_group(0);
+    for (int g = 0; g < ngroups; g++) {
+        init_group(g + 1);
+        grid.sync();
+        const int pe = (g + 1) * G < P ? (g + 1) * G : P;
+        const int64_t r0 = offs[(int64_t)g * G * nblocks_hist], r1 = offs[(int64_t)pe * nblocks_hist];
+        for (int64_t t0 = r0 + (int64_t)blockIdx.x * THREADS; t0 < r1; t0 += (int64_t)gstride) {
+            const int64_t r = t0 + threadIdx.x;
+            unsigned long long w[W];
+            bool pending = r < r1;
+            if (pending) {
+                if (W == 2) {
+                    int4 v = ld_stream_16(packed + r * 2);
+                    w[0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                    w[W - 1] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < W; i++) w[i] = (unsigned long long)ld_stream_8(packed + r * W + i);
+                }
+                if (w[0] == KEY_EMPTY) { flags[FL_SENTINEL] = 1; pending = false; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < W; i++) w[i] = 0;
+            }
+            uint64_t sl = __umul64hi(key_hash(w[0]), nslots);
+            int disp = 0;
+            while (pending) {
+                unsigned long long prev = atomicCAS(table + sl * W, KEY_EMPTY, w[0]);
+                if (prev == KEY_EMPTY) {
+#pragma unroll
+                    for (int i = 1; i < W; i++) table[sl * W + i] = w[i];
+                    pending = false;
+                } else if (prev == w[0]) {
+                    flags[FL_DUP] = 1;
+                    pending = false;
+                } else {
+                    if (++sl == nslots) sl = 0;
+                    if (++disp > MAX_DISP) { flags[FL_DISP] = 1; pending = false; }
+                }
+            }
         }
     }
 }
@@ -444,69 +647,58 @@ __device__ __forceinline__ void stage_words(char *staging, int tile_rows, bool w
     }
 }
 
-template <int PW, int BP>
-__device__ __forceinline__ void flush_words(const OutMap &O, const char *staging, int tile_rows, unsigned long long base, unsigned int cnt,
-                                            int32_t *flags) {
-    const unsigned long long end = base + cnt;
-    const uint8_t *sf = reinterpret_cast<const uint8_t *>(staging) + (size_t)(PW + BP) * tile_rows * 8;
-#pragma unroll 1
-    for (int q = 0; q < O.nout; q++) {
-        const bool probe_side = O.side[q] == 0;
-        const int j = probe_side ? O.word[q] : (O.word[q] == 0 ? 0 : PW + O.word[q] - 1);
-        const char *src = staging + (size_t)j * tile_rows * 8;
-        if (O.is32[q]) {
-            const unsigned int *s32 = reinterpret_cast<const unsigned int *>(src) + (O.half[q] == 1 ? 1 : 0);  // element i at s32[2*i]
-            int *dst = reinterpret_cast<int *>(O.data[q]);
-            // groups of 4 elements whose ADDRESS is 16-byte aligned (the column base only needs natural alignment)
-            const long long g0 = (long long)base - (long long)((((unsigned long long)(uintptr_t)dst >> 2) + base) & 3ULL);
-            const unsigned int groups = (unsigned int)(((long long)end - g0 + 3) >> 2);
-            for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
-                const long long g = g0 + 4LL * grp;
-                if (g >= (long long)base && g + 4 <= (long long)end) {
-                    const unsigned int l = (unsigned int)(g - base);
-                    int4 v;
-                    v.x = (int)s32[2 * l];
-                    v.y = (int)s32[2 * l + 2];
-                    v.z = (int)s32[2 * l + 4];
-                    v.w = (int)s32[2 * l + 6];
-                    st_stream_16(dst + g, v);
-                } else {
+// One element per lane: a warp reads 32 consecutive staged words (conflict-free) and writes one full, 128-byte
+// ALIGNED line of an INT column (or two lines of a BIGINT column).  The lane -> element mapping is shifted so that
+// line boundaries of the destination ADDRESS fall between warps (the column base only needs natural alignment);
+// partially covered lines occur only at the two ends of the tile's run.  Everything per element is (per-column base) +
+// compile-time offset: EPT unrolled stores plus one tail store for the `shift` elements the mapping pushed out.
+template <int PW, int BP, int NT, int EPT>
+__device__ __forceinline__ void flush_col(const OutMap &O, int q, const char *staging, unsigned long long base, int n, int32_t *flags) {
+    constexpr int tile_rows = NT * EPT;
+    const bool probe_side = O.side[q] == 0;
+    const int j = probe_side ? O.word[q] : (O.word[q] == 0 ? 0 : PW + O.word[q] - 1);
+    const char *src = staging + (size_t)j * tile_rows * 8;
+    const int tid = (int)threadIdx.x;
+    if (O.is32[q]) {
+        int *dst = reinterpret_cast<int *>(O.data[q]) + base;
+        const int l0 = tid - (int)(((unsigned long long)(uintptr_t)dst >> 2) & 31ULL);
+        const unsigned int *sp = reinterpret_cast<const unsigned int *>(src) + (O.half[q] == 1 ? 1 : 0) + 2 * l0;  // element l at [2*l]
+        int *dp = dst + l0;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        if (g + i >= (long long)base && g + i < (long long)end) st_stream_4(dst + g + i, (int)s32[2 * (unsigned int)(g + i - (long long)base)]);
-                }
-            }
-        } else {
-            const unsigned long long *s64 = reinterpret_cast<const unsigned long long *>(src);
-            long long *dst = reinterpret_cast<long long *>(O.data[q]);
-            const long long g0 = (long long)base - (long long)((((unsigned long long)(uintptr_t)dst >> 3) + base) & 1ULL);
-            const unsigned int groups = (unsigned int)(((long long)end - g0 + 1) >> 1);
-            for (unsigned int grp = threadIdx.x; grp < groups; grp += blockDim.x) {
-                const long long g = g0 + 2LL * grp;
-                if (g >= (long long)base && g + 2 <= (long long)end) {
-                    const unsigned int l = (unsigned int)(g - base);
-                    unsigned long long a = s64[l], b = s64[l + 1];
-                    int4 v;
-                    v.x = (int)(unsigned)a;
-                    v.y = (int)(unsigned)(a >> 32);
-                    v.z = (int)(unsigned)b;
-                    v.w = (int)(unsigned)(b >> 32);
-                    st_stream_16(dst + g, v);
-                } else {
+        for (int k = 0; k < EPT; k++)
+            if ((unsigned)(l0 + k * NT) < (unsigned)n) st_stream_4(dp + k * NT, (int)sp[2 * k * NT]);
+        if (l0 + EPT * NT < n) st_stream_4(dp + EPT * NT, (int)sp[2 * EPT * NT]);
+    } else {
+        long long *dst = reinterpret_cast<long long *>(O.data[q]) + base;
+        const int l0 = tid - (int)(((unsigned long long)(uintptr_t)dst >> 3) & 15ULL);
+        const unsigned long long *sp = reinterpret_cast<const unsigned long long *>(src) + l0;
+        long long *dp = dst + l0;
 #pragma unroll
-                    for (int i = 0; i < 2; i++)
-                        if (g + i >= (long long)base && g + i < (long long)end) st_stream_8(dst + g + i, (long long)s64[(unsigned int)(g + i - (long long)base)]);
-                }
-            }
-        }
-        if (O.nulls[q]) {  // NULL flags: only build-side columns of an outer join can be NULL here
-            const bool outer = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
-            for (unsigned long long g = base + threadIdx.x; g < end; g += blockDim.x)
-                O.nulls[q][g] = (!probe_side && outer) ? sf[(unsigned int)(g - base)] : 0;
-        } else if (!probe_side && (O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT)) {
-            if (threadIdx.x == 0) flags[FL_NULLOUT] = 1;  // rejected on the host before launch
-        }
+        for (int k = 0; k < EPT; k++)
+            if ((unsigned)(l0 + k * NT) < (unsigned)n) st_stream_8(dp + k * NT, (long long)sp[k * NT]);
+        if (l0 + EPT * NT < n) st_stream_8(dp + EPT * NT, (long long)sp[EPT * NT]);
     }
+    if (O.nulls[q]) {  // NULL flags: only build-side columns of an outer join can be NULL here
+        const uint8_t *sf = reinterpret_cast<const uint8_t *>(staging) + (size_t)(PW + BP) * tile_rows * 8;
+        const bool outer = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
+        uint8_t *nd = O.nulls[q] + base;
+#pragma unroll
+        for (int k = 0; k < EPT; k++)
+            if (tid + k * NT < n) nd[tid + k * NT] = (!probe_side && outer) ? sf[tid + k * NT] : 0;
+    } else if (!probe_side && (O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT)) {
+        if (tid == 0) flags[FL_NULLOUT] = 1;  // rejected on the host before launch
+    }
+}
+
+template <int PW, int BP, int NT, int EPT>
+__device__ __forceinline__ void flush_words(const OutMap &O, const char *staging, unsigned long long base, unsigned int cnt, int32_t *flags) {
+    const int n = (int)cnt;
+    // the first columns are unrolled: their descriptors become direct constant-bank operands
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+        if (q < O.nout) flush_col<PW, BP, NT, EPT>(O, q, staging, base, n, flags);
+#pragma unroll 1
+    for (int q = 8; q < O.nout; q++) flush_col<PW, BP, NT, EPT>(O, q, staging, base, n, flags);
 }
 
 static size_t stage_words_bytes(int PW, int BW, int tile_rows) {
@@ -707,7 +899,7 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_probe(const unsigned long lon
     }
     stage_words<RPT, PW, BP>(reinterpret_cast<char *>(probe_stage), TILE, want_flags, pw, bp, found, em, li);
     __syncthreads();
-    flush_words<PW, BP>(O, reinterpret_cast<const char *>(probe_stage), TILE, tile_base, tile_total, flags);
+    flush_words<PW, BP, THREADS, RPT>(O, reinterpret_cast<const char *>(probe_stage), tile_base, tile_total, flags);
 }
 
 // ------------------------------------------------------------------------------------------------ TMA-staged probe
@@ -861,7 +1053,7 @@ __global__ void __launch_bounds__(PT_THREADS, 3) k_fj_probe_tma(const unsigned l
         for (int k = 0; k < PT_RPT; k++) li[k] = cell[db][warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
         stage_words<PT_RPT, PW, BP>(staging, PT_TILE, O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT, pw, bp, found, em, li);
         __syncthreads();  // (C) the tile's output is dense in shared memory
-        flush_words<PW, BP>(O, staging, PT_TILE, tile_base[db], tile_total[db], flags);
+        flush_words<PW, BP, PT_THREADS, PT_RPT>(O, staging, tile_base[db], tile_total[db], flags);
         // no barrier needed here: the next staging writes come after the next iteration's (A) and (B)
     }
 }
@@ -875,6 +1067,7 @@ struct JoinFast {
     int P = 1;               // partitions (1 = table small enough to stay in L2 without partitioning)
     uint64_t nslots = 0;
     DevBuf table, flags, cursor;
-    int64_t part_bytes = 32ll << 20;
+    int64_t part_bytes = 16ll << 20;
     int64_t sub_batch = 256ll << 20;  // probe rows per partition+probe round (bounds scratch memory)
+    int64_t part_min_rows = 1ll << 20;  // smaller probe batches skip the partitioning passes
 };

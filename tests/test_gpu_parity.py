@@ -166,6 +166,8 @@ def small_partitions(monkeypatch):
     """Force the radix-partitioned path (P > 1, several sub-batches) at test sizes."""
     monkeypatch.setenv("GSQL_JOIN_PART_BYTES", str(64 << 10))
     monkeypatch.setenv("GSQL_JOIN_SUB_BATCH", "30000")
+    monkeypatch.setenv("GSQL_JOIN_PART_MIN_ROWS", "0")
+    monkeypatch.setenv("GSQL_JOIN_BUILD_GROUP_BYTES", str(64 << 10))   # several groups in the fused build
 
 
 def _unique_key_tables(nb, npr, key_space, key_dtype, n_build_pay, n_probe_pay, seed):
@@ -208,11 +210,34 @@ def test_fast_join_partitioned_vs_oracle(gu, small_partitions, jt, shape):
 def test_fast_join_host_pipeline(gu, monkeypatch, jt):
     """Host batches >= 1M rows go through the sliced H2D / compute / D2H pipeline (5 slices here)."""
     monkeypatch.setenv("GSQL_JOIN_PART_BYTES", str(256 << 10))
+    monkeypatch.setenv("GSQL_JOIN_PART_MIN_ROWS", "0")
     monkeypatch.setenv("GSQL_JOIN_HOST_SLICE", "300000")
     outer, inner, kc = _unique_key_tables(100_000, 1_300_000, 150_000, np.int64, 2, 2, seed=1200 + jt)
     spec = orc.JoinSpec(jt, [kc], [0], [orc.T_INT64])
     exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
     assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="host")) == exp
+
+
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_ANTI])
+@pytest.mark.parametrize("fused_build", ["1", "0"])
+def test_fast_join_small_batch_skips_partitioning(gu, monkeypatch, jt, fused_build):
+    """A partitioned table (P > 1) answers a batch below GSQL_JOIN_PART_MIN_ROWS by probing it directly, and a batch
+    above it through the hist / scatter / probe passes; both builds (fused cooperative, init + insert) agree."""
+    monkeypatch.setenv("GSQL_JOIN_PART_BYTES", str(64 << 10))
+    monkeypatch.setenv("GSQL_JOIN_PART_MIN_ROWS", "50000")
+    monkeypatch.setenv("GSQL_JOIN_BUILD_FUSED", fused_build)
+    monkeypatch.setenv("GSQL_JOIN_BUILD_GROUP_BYTES", str(64 << 10))
+    from galaxysql_b200 import api, native as N
+    outer, inner, kc = _unique_key_tables(40_000, 120_000, 60_000, np.int64, 2, 2, seed=4100 + jt)
+    spec = orc.JoinSpec(jt, [kc], [0], [orc.T_INT64])
+    j = api.HashJoin(gu.ctx(), jt, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    j.build_consume(inner)
+    j.build_finish()
+    assert j.info().fast_path == 1 and j.info().partitions > 1
+    small = [(d[:20_000], None) for d, _ in outer]
+    assert ku.rows_multiset(gu.to_numpy(j.probe(small))) == ku.rows_multiset(orc.hash_join(spec, small, inner))
+    assert ku.rows_multiset(gu.to_numpy(j.probe(outer))) == ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    j.close()
 
 
 def test_fast_join_is_taken_and_falls_back(gu, small_partitions):
