@@ -49,15 +49,26 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region.  In-process NVML polling (cheap driver calls) is
+    preferred: a `nvidia-smi -lms` loop stalls the GPU for milliseconds per query, which at ~30 ms per step showed up
+    as ~4 ms of idle time per step.  GSQL_BENCH_CLOCKS=smi|nvml|off overrides."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
         self.lines = []
         self.proc = None
+        self.nvml = None
+        self.mode = os.environ.get("GSQL_BENCH_CLOCKS", "nvml")
+        self._stop = threading.Event()
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml" and self._start_nvml():
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -66,11 +77,62 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _start_nvml(self) -> bool:
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            reasons_fn(h)
+        except Exception:
+            return False
+        self.nvml = (pynvml, h, smax, reasons_fn)
+
+        def poll():
+            while not self._stop.is_set():
+                try:
+                    sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                    rs = int(reasons_fn(h))
+                    self.lines.append((time.time(), sm, rs))
+                except Exception:
+                    pass
+                self._stop.wait(0.02)
+        self.t = threading.Thread(target=poll, daemon=True)
+        self.t.start()
+        return True
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
+    def _stop_nvml(self, t0: float, t1: float):
+        self._stop.set()
+        self.t.join(timeout=1.0)
+        _, _, smax, _ = self.nvml
+        sm, reasons = [], set()
+        for ts, mhz, rs in self.lines:
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(float(mhz))
+            for bit, nm in self.NVML_REASONS.items():
+                if rs & bit:
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(smax), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml, 20 ms period"}
+
     def stop(self, t0: float, t1: float):
+        if self.nvml:
+            return self._stop_nvml(t0, t1)
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -299,10 +361,10 @@ def run_ours(args):
     probe_rows_rank = n_out
     peak, peak_src = measured_peak_gbs()
     achieved = PROBE_ALG_BYTES * probe_rows_rank / (probe_ms / 1000.0) / 1e9 if probe_ms > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_fj_probe launch over 1 B probe rows (unpartitioned default),
-    # from the `ncu --set full` capture summarised in profiles/r01_ncu_summary.md (prof_r01h): 141.97 + 31.98 GB.  Every
-    # random 16-byte table read costs a ~128-byte HBM fetch on this part, so traffic is ~2.6x the algorithmic bytes.
-    traffic = 173.95e9 * (probe_rows_rank / 1e9) if state["info"].partitions == 1 else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of the probe-phase launches over 1 B probe rows, from the `ncu --set full`
+    # captures summarised in profiles/r01_ncu_summary.md.  Radix mode (prof_r01i/k): k_fj_hist 8.0 + k_fj_scatter 32.5 +
+    # k_fj_probe 51.1 GB.  One partition (prof_r01h): 173.95 GB — every random 16-byte table read costs a ~128-byte HBM fetch.
+    traffic = (173.95e9 if state["info"].partitions == 1 else 91.6e9) * (probe_rows_rank / 1e9)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "+".join(sorted(probe_kernels)), "kernel_ms_per_step": probe_ms,
                 "algorithmic_bytes_per_probe_row": PROBE_ALG_BYTES, "peak_source": peak_src,

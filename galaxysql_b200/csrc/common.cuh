@@ -264,6 +264,13 @@ __device__ __forceinline__ int4 ld_keep_16(const void *p, uint64_t pol) {
                  : "l"(p), "l"(pol));
     return v;
 }
+__device__ __forceinline__ int4 ld_keep_16_na(const void *p, uint64_t pol) {  // same, without allocating an L1 line
+    int4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ unsigned long long ld_keep_8(const void *p, uint64_t pol) {
     unsigned long long v;
     asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));

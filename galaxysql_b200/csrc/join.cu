@@ -913,6 +913,7 @@ static void fast_out_map(gsql_join *j, const ProbeParams &PP, fj::OutMap *O) {
     memset(O, 0, sizeof(*O));
     O->nout = j->nout;
     O->join_type = j->spec.join_type;
+    O->lookup_mode = (int32_t)env_i64("GSQL_JOIN_LOOKUP_MODE", 1);
     for (int q = 0; q < j->nout; q++) {
         const fj::Layout &L = j->out_side[q] == SIDE_PROBE ? F.pl : F.bl;
         O->data[q] = PP.out[q].data;
@@ -967,6 +968,34 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         }                                                                                                                                    \
         fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::PT_THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
                                                                                ticket, F.flags.as<int32_t>());                               \
+    }
+        FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
+        FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)
+        FJ_PROBE_CASE(3, 1) FJ_PROBE_CASE(3, 2) FJ_PROBE_CASE(3, 3) FJ_PROBE_CASE(3, 4)
+        FJ_PROBE_CASE(4, 1) FJ_PROBE_CASE(4, 2) FJ_PROBE_CASE(4, 3) FJ_PROBE_CASE(4, 4)
+#undef FJ_PROBE_CASE
+    } else if (src && env_i64("GSQL_JOIN_PROBE_PIPE", 0) && fj::probe_pipe_smem_bytes(PW, BW) + 2048 <= 113 * 1024) {
+        // persistent blocks, next tile's packed rows prefetched with cp.async (two blocks per SM must still fit)
+        GSQL_CUDA(ctx, cudaMemsetAsync(ticket, 0, 8, ctx->stream));
+        KernelScope ks(ctx, "join_fast_probe");
+        size_t smem = fj::probe_pipe_smem_bytes(PW, BW);
+        int64_t ntiles = div_up(m, fj::TILE);
+        int grid = (int)(ntiles < (int64_t)ctx->sm_count * 2 ? ntiles : (int64_t)ctx->sm_count * 2);
+#define FJ_PROBE_CASE(PWv, BWv)                                                                                                             \
+    if (PW == PWv && BW == BWv) {                                                                                                           \
+        static int attr_smem = 0;                                                                                                           \
+        if ((int)smem > attr_smem) {                                                                                                        \
+            GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_pipe<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+            attr_smem = (int)smem;                                                                                                          \
+        }                                                                                                                                   \
+        int per_sm = 0;                                                                                                                     \
+        GSQL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fj::k_fj_probe_pipe<PWv, BWv>, fj::THREADS, smem));           \
+        if (per_sm < 1) per_sm = 1;                                                                                                         \
+        if (per_sm > 2) per_sm = 2;                                                                                                         \
+        if (env_i64("GSQL_DEBUG", 0)) fprintf(stderr, "k_fj_probe_pipe<%d,%d>: smem %zu, %d blocks/SM\n", PWv, BWv, smem, per_sm);          \
+        grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);                                  \
+        fj::k_fj_probe_pipe<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
+                                                                               ticket, F.flags.as<int32_t>());                              \
     }
         FJ_PROBE_CASE(1, 1) FJ_PROBE_CASE(1, 2) FJ_PROBE_CASE(1, 3) FJ_PROBE_CASE(1, 4)
         FJ_PROBE_CASE(2, 1) FJ_PROBE_CASE(2, 2) FJ_PROBE_CASE(2, 3) FJ_PROBE_CASE(2, 4)

@@ -242,6 +242,10 @@ __device__ __forceinline__ void cp_async_8(void *smem_dst, const void *gsrc) {
 __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async_16_hint(void *smem_dst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "l"(pol)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -591,6 +595,7 @@ struct OutMap {
     int32_t stage_off[GSQL_MAX_COLS * 2];   // byte offset of column q inside a tile's shared-memory output staging
     int32_t stage_null_off[GSQL_MAX_COLS * 2];
     int32_t stage_bytes;                    // staging bytes per tile (PT_TILE rows)
+    int32_t lookup_mode;                    // 0: ld.global.nc  1: + L1::no_allocate  2: cp.async gather through shared memory
 };
 
 template <int W>
@@ -701,6 +706,10 @@ __device__ __forceinline__ void flush_words(const OutMap &O, const char *staging
     for (int q = 8; q < O.nout; q++) flush_col<PW, BP, NT, EPT>(O, q, staging, base, n, flags);
 }
 
+__host__ __device__ constexpr size_t stage_words_bytes_c(int PW, int BW, int tile_rows) {
+    return (size_t)(PW + (BW > 1 ? BW - 1 : 1)) * tile_rows * 8 + (size_t)tile_rows;
+}
+static size_t probe_pipe_smem_bytes(int PW, int BW) { return ((stage_words_bytes_c(PW, BW, 2048) + 15) & ~(size_t)15) + (size_t)2048 * PW * 8; }
 static size_t stage_words_bytes(int PW, int BW, int tile_rows) {
     int BP = BW > 1 ? BW - 1 : 1;
     return (size_t)(PW + BP) * tile_rows * 8 + (size_t)tile_rows;
@@ -746,7 +755,8 @@ __device__ __forceinline__ void write_rows(const OutMap &O, const unsigned long 
 // instead of (sum over rows of the warp-wide longest sequence).  KEY_EMPTY rows (padding / the unbuildable key) never match.
 template <int R, int PW, int BW, int BP>
 __device__ __forceinline__ void lookup_rounds(const unsigned long long *__restrict__ table, uint64_t nslots, uint64_t pol,
-                                              const unsigned long long (&pw)[R][PW], unsigned long long (&bp)[R][BP], bool (&found)[R]) {
+                                              const unsigned long long (&pw)[R][PW], unsigned long long (&bp)[R][BP], bool (&found)[R],
+                                              int mode = 0, int4 *gbuf = nullptr) {
     uint64_t slot[R];
     unsigned long long tk[R];
     bool pending[R];
@@ -756,14 +766,29 @@ __device__ __forceinline__ void lookup_rounds(const unsigned long long *__restri
 #pragma unroll
         for (int i = 0; i < BP; i++) bp[k][i] = 0;
     }
+    if (BW == 2 && mode == 2) {
+        // 16-byte slots gathered with cp.async.cg: the reads bypass L1 (no line is reserved per outstanding miss), land in
+        // this thread's own cells of the tile's shared-memory area and are picked up after one wait
 #pragma unroll
-    for (int k = 0; k < R; k++) {
-        if (BW == 2) {
-            int4 v = ld_keep_16(table + slot[k] * 2, pol);
+        for (int k = 0; k < R; k++) cp_async_16_hint(gbuf + k * THREADS + threadIdx.x, table + slot[k] * 2, pol);
+        cp_async_commit();
+        cp_async_wait<0>();
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            int4 v = gbuf[k * THREADS + threadIdx.x];
             tk[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
             bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
-        } else {
-            tk[k] = ld_keep_8(table + slot[k] * BW, pol);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            if (BW == 2) {
+                int4 v = mode == 1 ? ld_keep_16_na(table + slot[k] * 2, pol) : ld_keep_16(table + slot[k] * 2, pol);
+                tk[k] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                bp[k][0] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+            } else {
+                tk[k] = ld_keep_8(table + slot[k] * BW, pol);
+            }
         }
     }
     bool any = false;
@@ -803,23 +828,88 @@ __device__ __forceinline__ void lookup_rounds(const unsigned long long *__restri
     }
 }
 
+struct ProbeShared {
+    unsigned int cell[THREADS / 32][RPT];
+    unsigned long long tile_base;
+    unsigned int tile_total;
+};
+
+// Steps 2-4 of a probe tile, given the RPT packed probe rows of this thread in pw (rows beyond the batch carry KEY_EMPTY
+// and live[k] = false): table lookups, emit decision, tile-wide compaction, staged column flush.
+template <int PW, int BW>
+__device__ __forceinline__ void probe_tile(unsigned long long (&pw)[RPT][PW], const bool (&live)[RPT], const unsigned long long *__restrict__ table,
+                                           uint64_t nslots, uint64_t pol, const OutMap &O, unsigned long long *cursor, int32_t *flags,
+                                           ProbeShared &sh, unsigned char *probe_stage) {
+    constexpr int BP = BW > 1 ? BW - 1 : 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long bp[RPT][BP];  // build payload words (the build key equals the probe key on a match)
+    unsigned int ballot[RPT];
+    bool found[RPT];
+    // 2. table lookups in rounds (one L2-resident read per row per round, all rows of the thread in flight)
+    lookup_rounds<RPT, PW, BW, BP>(table, nslots, pol, pw, bp, found, O.lookup_mode, reinterpret_cast<int4 *>(probe_stage));
+    // 3. which rows emit (AbstractBufferedJoinExec.nextRows:185-264 for unique build keys, no NULLs)
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        bool emit;
+        switch (O.join_type) {
+        case GSQL_JOIN_INNER: emit = found[k]; break;
+        case GSQL_JOIN_SEMI: emit = found[k]; break;
+        case GSQL_JOIN_ANTI: emit = !found[k]; break;
+        default: emit = true; break;  // LEFT / RIGHT: unmatched probe rows are NULL-padded
+        }
+        emit = emit && live[k];
+        ballot[k] = __ballot_sync(0xffffffffu, emit);
+        if (lane == 0) sh.cell[warp][k] = __popc(ballot[k]);
+    }
+    __syncthreads();
+    unsigned long long my_base = 0;
+    if (warp == 0) {  // exclusive scan over the 64 (warp, k) cells + one cursor bump for the tile
+        constexpr int CELLS = (THREADS / 32) * RPT;
+        unsigned int *flat = &sh.cell[0][0];
+        unsigned int a = flat[lane * 2], b = flat[lane * 2 + 1];
+        unsigned int sum = a + b, incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        unsigned int excl = incl - sum;
+        unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 0) {  // the cursor bump's round trip overlaps the staging below: its result is only published after it
+            my_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
+            sh.tile_total = total;
+        }
+        flat[lane * 2] = excl;
+        flat[lane * 2 + 1] = excl + a;
+        static_assert(CELLS == 64, "cell scan assumes 64 cells");
+    }
+    __syncthreads();
+    // 4. compact the tile's rows into shared memory (word arrays), then flush the columns with aligned full-line stores
+    const bool want_flags = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
+    bool em[RPT];
+    unsigned int li[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; k++) {
+        em[k] = (ballot[k] >> lane) & 1u;
+        li[k] = sh.cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+    }
+    stage_words<RPT, PW, BP>(reinterpret_cast<char *>(probe_stage), TILE, want_flags, pw, bp, found, em, li);
+    if (threadIdx.x == 0) sh.tile_base = my_base;
+    __syncthreads();
+    flush_words<PW, BP, THREADS, RPT>(O, reinterpret_cast<const char *>(probe_stage), sh.tile_base, sh.tile_total, flags);
+}
+
+// One tile per block; probe rows come from the input columns (packed == nullptr) or from packed rows.
 template <int PW, int BW>
 __global__ void __launch_bounds__(THREADS, 2) k_fj_probe(const unsigned long long *__restrict__ packed, const __grid_constant__ DColSet cols,
                                                       const __grid_constant__ Layout L, int64_t n, const unsigned long long *__restrict__ table,
                                                       uint64_t nslots, const __grid_constant__ OutMap O, unsigned long long *cursor, int32_t *flags) {
-    __shared__ unsigned int cell[THREADS / 32][RPT];
-    __shared__ unsigned long long tile_base;
-    __shared__ unsigned int tile_total;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ ProbeShared sh;
+    extern __shared__ __align__(16) unsigned char probe_stage[];
     const uint64_t pol = l2_policy_evict_last();
     const int64_t t0 = (int64_t)blockIdx.x * TILE;
-    constexpr int BP = BW > 1 ? BW - 1 : 1;
-
     unsigned long long pw[RPT][PW];
-    unsigned long long bp[RPT][BP];  // build payload words (the build key equals the probe key on a match)
-    unsigned int ballot[RPT];
-    bool found[RPT];
-
+    bool live[RPT];
     // 1. stream the probe rows in (all RPT loads in flight)
     if (packed) {
 #pragma unroll
@@ -842,64 +932,90 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_probe(const unsigned long lon
     } else {
         pack_tile<PW>(cols, L, t0 + threadIdx.x, n, pw);
     }
-    // 2. table lookups in rounds (one L2-resident read per row per round, all rows of the thread in flight)
-#pragma unroll
-    for (int k = 0; k < RPT; k++)
-        if (t0 + k * THREADS + threadIdx.x >= n) pw[k][0] = KEY_EMPTY;
-    lookup_rounds<RPT, PW, BW, BP>(table, nslots, pol, pw, bp, found);
-    // 3. which rows emit (AbstractBufferedJoinExec.nextRows:185-264 for unique build keys, no NULLs)
-    unsigned int my_total = 0;
 #pragma unroll
     for (int k = 0; k < RPT; k++) {
-        int64_t r = t0 + k * THREADS + threadIdx.x;
-        bool live = r < n;
-        bool emit;
-        switch (O.join_type) {
-        case GSQL_JOIN_INNER: emit = found[k]; break;
-        case GSQL_JOIN_SEMI: emit = found[k]; break;
-        case GSQL_JOIN_ANTI: emit = !found[k]; break;
-        default: emit = true; break;  // LEFT / RIGHT: unmatched probe rows are NULL-padded
-        }
-        emit = emit && live;
-        ballot[k] = __ballot_sync(0xffffffffu, emit);
-        if (lane == 0) cell[warp][k] = __popc(ballot[k]);
-        my_total += emit;
+        live[k] = t0 + k * THREADS + threadIdx.x < n;
+        if (!live[k]) pw[k][0] = KEY_EMPTY;
     }
-    __syncthreads();
-    if (warp == 0) {  // exclusive scan over the 64 (warp, k) cells + one cursor bump for the tile
-        constexpr int CELLS = (THREADS / 32) * RPT;
-        unsigned int *flat = &cell[0][0];
-        unsigned int a = flat[lane * 2], b = flat[lane * 2 + 1];
-        unsigned int sum = a + b, incl = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        unsigned int excl = incl - sum;
-        unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-        if (lane == 0) {
-            tile_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ULL;
-            tile_total = total;
-        }
-        flat[lane * 2] = excl;
-        flat[lane * 2 + 1] = excl + a;
-        static_assert(CELLS == 64, "cell scan assumes 64 cells");
-    }
-    __syncthreads();
-    // 4. compact the tile's rows into shared memory (word arrays), then flush the columns with aligned 16-byte stores
+    probe_tile<PW, BW>(pw, live, table, nslots, pol, O, cursor, flags, sh, probe_stage);
+}
+
+// Persistent variant for packed probe rows (the partitioned mode): blocks walk the tiles in index order (all resident
+// blocks stay on neighbouring tiles, i.e. on the same L2-resident table slice) and the packed rows of the block's NEXT
+// tile are fetched with cp.async into a shared-memory input buffer while the current tile is looked up, compacted and
+// flushed — the HBM latency of the row stream leaves the per-tile dependency chain.  Each thread copies and reads back
+// only its own rows, so the single input buffer is refilled as soon as the thread has moved its rows to registers.
+template <int PW, int BW>
+__global__ void __launch_bounds__(THREADS, 2) k_fj_probe_pipe(const unsigned long long *__restrict__ packed, int64_t n,
+                                                           const unsigned long long *__restrict__ table, uint64_t nslots,
+                                                           const __grid_constant__ OutMap O, unsigned long long *cursor,
+                                                           unsigned long long *ticket, int32_t *flags) {
+    __shared__ ProbeShared sh;
     extern __shared__ __align__(16) unsigned char probe_stage[];
-    const bool want_flags = O.join_type == GSQL_JOIN_LEFT || O.join_type == GSQL_JOIN_RIGHT;
-    bool em[RPT];
-    unsigned int li[RPT];
+    unsigned long long *inbuf = reinterpret_cast<unsigned long long *>(probe_stage + ((stage_words_bytes_c(PW, BW, TILE) + 15) & ~(size_t)15));
+    const uint64_t pol = l2_policy_evict_last();
+    const int64_t ntiles = (n + TILE - 1) / TILE;
+    const unsigned tid = threadIdx.x;
+    auto prefetch = [&](int64_t tile) {
+        const int64_t t0 = tile * TILE;
+        const unsigned long long *gp = packed + (t0 + tid) * PW;
+        unsigned long long *sp = inbuf + (size_t)tid * PW;
+        const int n_tile = (int)(n - t0 < TILE ? n - t0 : TILE);
 #pragma unroll
-    for (int k = 0; k < RPT; k++) {
-        em[k] = (ballot[k] >> lane) & 1u;
-        li[k] = cell[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+        for (int k = 0; k < RPT; k++) {
+            if ((int)(k * THREADS + tid) < n_tile) {
+                if (PW == 2) {
+                    cp_async_16(sp + (size_t)k * THREADS * 2, gp + (size_t)k * THREADS * 2);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PW; i++) cp_async_8(sp + (size_t)k * THREADS * PW + i, gp + (size_t)k * THREADS * PW + i);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // Tiles are handed out through a global ticket, one tile ahead (the prefetch needs the next tile's index): with a
+    // static tile -> block map a block that falls behind keeps reading a table slice the others have left, misses L2,
+    // falls further behind (measured: 2x the DRAM reads of the one-tile-per-block kernel).
+    __shared__ long long nxt[2];
+    if (tid == 0) {
+        nxt[0] = (long long)atomicAdd(ticket, 1ULL);
+        nxt[1] = (long long)atomicAdd(ticket, 1ULL);
     }
-    stage_words<RPT, PW, BP>(reinterpret_cast<char *>(probe_stage), TILE, want_flags, pw, bp, found, em, li);
     __syncthreads();
-    flush_words<PW, BP, THREADS, RPT>(O, reinterpret_cast<const char *>(probe_stage), tile_base, tile_total, flags);
+    int64_t tile = nxt[0];
+    if (tile < ntiles) prefetch(tile);
+    for (int it = 0; tile < ntiles; it++) {
+        const int64_t next = nxt[(it + 1) & 1];
+        const int64_t t0 = tile * TILE;
+        const int n_tile = (int)(n - t0 < TILE ? n - t0 : TILE);
+        unsigned long long pw[RPT][PW];
+        bool live[RPT];
+        cp_async_wait<0>();
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            live[k] = (int)(k * THREADS + tid) < n_tile;
+            if (live[k]) {
+                if (PW == 2) {
+                    int4 v = *reinterpret_cast<const int4 *>(inbuf + ((size_t)k * THREADS + tid) * 2);
+                    pw[k][0] = ((unsigned long long)(unsigned)v.y << 32) | (unsigned)v.x;
+                    pw[k][PW - 1] = ((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PW; i++) pw[k][i] = inbuf[((size_t)k * THREADS + tid) * PW + i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PW; i++) pw[k][i] = 0;
+                pw[k][0] = KEY_EMPTY;
+            }
+        }
+        if (next < ntiles) prefetch(next);
+        if (tid == 0) nxt[it & 1] = (long long)atomicAdd(ticket, 1ULL);  // slot of `tile`: everyone read it before the last barrier
+        probe_tile<PW, BW>(pw, live, table, nslots, pol, O, cursor, flags, sh, probe_stage);
+        __syncthreads();  // the staging area and the scan cells are rewritten by the next tile
+        tile = next;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ TMA-staged probe
