@@ -311,17 +311,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the sampler is started BEFORE the warm-up so that the timed region follows the warm-up back to back: an idle gap
+    # here (there used to be a 0.3 s sleep) lets the GPU drop out of its boost state and the first timed steps pay the ramp
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
     ctx.profile(True)
     ctx.profile_reset()
     launches0 = ctx.launch_count
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.time()

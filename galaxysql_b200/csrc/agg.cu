@@ -11,8 +11,9 @@
 // keys and every accumulator are columnar arrays indexed by group id, updated with native L2 atomics
 // (int64 add, fp64 add, int64 min/max on an order-preserving transform).  SUM(int|bigint) is exact 128-bit
 // (lo/hi with carry), which equals the reference's long-with-overflow-escape-to-DECIMAL result.
-// Two specialisations sit in front of the generic kernel (agg_fast.cuh): a shared-memory privatised table for
-// low-cardinality group-bys and a key-in-slot table for single-integer-key high-cardinality group-bys.
+// Two adaptive specialisations sit in front of the generic kernel: lane-private shared-memory accumulators for a
+// handful of groups (agg_lane.cuh, the TPC-H Q1 shape) and warp-private shared-memory tables for tens of groups
+// (agg_fast.cuh); rows whose key does not fit their small tables take the generic path inside the same kernel.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -411,6 +412,7 @@ int agg_out_type(int kind, int in_type) {
 }  // namespace
 
 #include "agg_fast.cuh"
+#include "agg_lane.cuh"
 
 struct gsql_agg {
     gsql_ctx *ctx;
@@ -431,6 +433,8 @@ struct gsql_agg {
     DevBuf out_data[GSQL_MAX_COLS], out_nulls[GSQL_MAX_COLS];
     int64_t cursor = 0;
     AggFast fast;
+    AggLane lane;
+    int64_t fallback_total = 0;  // counters[C_FALLBACK] as of the last read (cumulative on the device)
 };
 
 static int64_t init_value(int kind) {
@@ -576,7 +580,10 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     }
     cudaSetDevice(ctx->device);
     agg_fast_plan(&a->fast, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    agg_lane_check(&a->lane, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
+    if ((getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) || (getenv("GSQL_AGG_NO_LANE") && atoi(getenv("GSQL_AGG_NO_LANE"))))
+        a->lane.shape_ok = a->lane.enabled = false;
     a->slack = (int64_t)ctx->sm_count * 2048 + 1024 + (int64_t)ctx->sm_count * 2 * 1024;  // + CTA-table merges of the smem path
     int64_t gcap = s.expected_groups > 0 ? s.expected_groups : 1024;
     if (gcap < 65536) gcap = 65536;
@@ -628,7 +635,24 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     DevBuf pending;  // overflow rows being re-run
     bool first = true;
     while (true) {
-        if (first && a->fast.eligible && a->fast.enabled) {  // shared-memory privatised tables (low-cardinality shapes)
+        // three kernels, most specialised first: lane-private accumulators (a handful of groups), warp-private
+        // shared-memory tables (tens of groups), the generic global table; the first two are adaptive
+        LanePlan LP;
+        const bool use_lane = first && a->lane.shape_ok && a->lane.enabled &&
+                              agg_lane_plan(&LP, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type, P.in);
+        const bool use_smem = !use_lane && first && a->fast.eligible && a->fast.enabled;
+        if (use_lane) {
+            KernelScope ks(ctx, "agg_lane");
+            int64_t steps = div_up(P.rows, 32 * LA_R * LA_WARPS);
+            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count, steps);
+            if (grid < 1) grid = 1;
+            static int attr_smem = 0;
+            if (LP.total > attr_smem) {
+                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
+                attr_smem = LP.total;
+            }
+            k_agg_lane<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
+        } else if (use_smem) {
             KernelScope ks(ctx, "agg_smem");
             int64_t warps = div_up(P.rows, 32);
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, div_up(warps, AF_THREADS / 32));
@@ -646,10 +670,18 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         GSQL_CUDA(ctx, cudaGetLastError());
         unsigned long long h[C_COUNT];
         GSQL_TRY(agg_read_counters(a, h));
-        if (first && a->fast.eligible && a->fast.enabled) {  // adaptive: stop when the CTA tables do not hold the key set
-            a->fast.rows_seen += P.rows;
-            a->fast.rows_fallback = (int64_t)h[C_FALLBACK];
-            if (a->fast.rows_seen >= (1 << 16) && a->fast.rows_fallback * 8 > a->fast.rows_seen) a->fast.enabled = false;
+        {  // adaptive: stop using a privatised kernel when its small tables do not hold the key set
+            const int64_t fell = (int64_t)h[C_FALLBACK] - a->fallback_total;
+            a->fallback_total = (int64_t)h[C_FALLBACK];
+            if (use_lane) {
+                a->lane.rows_seen += P.rows;
+                a->lane.rows_fallback += fell;
+                if (a->lane.rows_seen >= (1 << 16) && a->lane.rows_fallback * 8 > a->lane.rows_seen) a->lane.enabled = false;
+            } else if (use_smem) {
+                a->fast.rows_seen += P.rows;
+                a->fast.rows_fallback += fell;
+                if (a->fast.rows_seen >= (1 << 16) && a->fast.rows_fallback * 8 > a->fast.rows_seen) a->fast.enabled = false;
+            }
         }
         first = false;
         a->ngroups = (int64_t)h[C_NGROUPS];

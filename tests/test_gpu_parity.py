@@ -405,6 +405,60 @@ def test_agg_q1_shape_fused_project_filter(gu):
         gu.approx_rows_equal(got, exp, float_cols=[2, 3, 4, 5, 6, 7, 8], key_cols=[0, 1], rtol=RTOL)
 
 
+@pytest.mark.parametrize("path", ["lane", "smem", "generic"])
+@pytest.mark.parametrize("ngroups", [1, 5, 13, 40])
+def test_agg_low_cardinality_paths_agree_with_oracle(gu, monkeypatch, path, ngroups):
+    """The three aggregation kernels (lane-private accumulators, warp-private shared-memory tables, global table) give the
+    oracle's groups on a low-cardinality shape with NULLs in keys and values, every aggregate kind, a nullable INT key
+    next to a DOUBLE key, several batches.  40 groups overflow the 16-slot warp dictionaries of the lane kernel: rows
+    take its in-kernel generic fallback and the handle adapts to the next kernel on the following batches."""
+    if path != "lane":
+        monkeypatch.setenv("GSQL_AGG_NO_LANE", "1")
+    if path == "generic":
+        monkeypatch.setenv("GSQL_AGG_NO_FAST", "1")
+    n = 300_000
+    k1 = (ku.rand_u64(n, 31) % np.uint64(ngroups)).astype(np.int32) - 2
+    k2 = ((ku.rand_u64(n, 32) % np.uint64(2)).astype(np.float64) - 0.5) * 3.0
+    v = (ku.rand_u64(n, 33) % np.uint64(100_000)).astype(np.float64) / 7.0
+    w = (ku.rand_u64(n, 34) % np.uint64(1000)).astype(np.int64) - 500
+    d = (ku.rand_u64(n, 35) % np.uint64(90)).astype(np.int32)
+    cols = [ku.with_nulls(k1, 0.03, 36), (k2, None), ku.with_nulls(v, 0.05, 37), ku.with_nulls(w, 0.02, 38), (d, None)]
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_COUNT, [2]), orc.AggCall(orc.AGG_COUNT, [2, 3]), orc.AggCall(orc.AGG_SUM, [2]),
+            orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_MIN, [2]), orc.AggCall(orc.AGG_MAX, [3]), orc.AggCall(orc.AGG_SUM0, [3]),
+            orc.AggCall(orc.AGG_MIN, [4]), orc.AggCall(orc.AGG_MAX, [2])]
+    for groups in ([0, 1], [0], []):
+        exp = orc.hash_agg(cols, groups, aggs, 64)
+        got = gu.gpu_hash_agg(cols, groups, aggs, 64, mem="device", batches=4)
+        nk = len(groups)
+        gu.approx_rows_equal(got, exp, float_cols=[nk + 3, nk + 4, nk + 5, nk + 9], key_cols=list(range(nk)), rtol=RTOL)
+
+
+def test_agg_lane_kernel_is_taken_for_q1_shape(gu):
+    """The Q1 shape (6 groups, 8 aggregates over plain DOUBLE columns) runs on k_agg_lane: the context's kernel profile
+    shows it, and no row leaves it for the generic path."""
+    from galaxysql_b200 import api, native as N
+    n = 500_000
+    flag = (ku.rand_u64(n, 41) % np.uint64(3)).astype(np.int32)
+    status = (ku.rand_u64(n, 42) % np.uint64(2)).astype(np.int32)
+    qty = ((ku.rand_u64(n, 43) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
+    price = ((ku.rand_u64(n, 44) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    cols = [(flag, None), (status, None), (qty, None), (price, None)]
+    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_AVG, [2]), (N.AGG_AVG, [3]), (N.AGG_COUNT_STAR, [])]
+    ctx = gu.ctx()
+    ctx.profile(True)
+    ctx.profile_reset()
+    a = api.HashAgg(ctx, [0, 0, 2, 2], [0, 1], aggs, 8)
+    a.consume(gu.to_device(cols))
+    got = gu.to_numpy(a.result(N.MEM_DEVICE))
+    a.close()
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    assert "agg_lane" in prof and "agg_smem" not in prof and "agg_consume" not in prof, prof
+    oaggs = [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_AVG, [3]),
+             orc.AggCall(orc.AGG_COUNT_STAR)]
+    gu.approx_rows_equal(got, orc.hash_agg(cols, [0, 1], oaggs, 8), float_cols=[2, 3, 4, 5], key_cols=[0, 1], rtol=RTOL)
+
+
 def test_agg_smem_path_adapts_to_high_cardinality(gu):
     """The shared-memory path must stay correct when the key set does not fit the CTA tables (rows bypass them)."""
     n = 400_000

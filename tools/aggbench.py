@@ -13,6 +13,8 @@ def run(name, cols, types, groups, aggs, expected, bytes_per_row, reps=3):
     rows = cols[0].numel()
     best = None
     for i in range(reps + 1):
+        if i == reps:
+            ctx.profile(True); ctx.profile_reset()
         a = api.HashAgg(ctx, types, groups, aggs, expected)
         ctx.sync(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -23,6 +25,7 @@ def run(name, cols, types, groups, aggs, expected, bytes_per_row, reps=3):
         a.close()
         if i > 0 and (best is None or dt < best):
             best = dt
+    print({k: round(v[1], 3) for k, v in ctx.profile_dump().items()}); ctx.profile(False)
     print(f"{name}: {rows} rows, {n} groups: {best*1e3:.2f} ms  {rows/best/1e9:.2f} Grows/s  {rows*bytes_per_row/best/1e9:.0f} GB/s algorithmic", flush=True)
 
 

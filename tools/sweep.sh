@@ -1,5 +1,4 @@
 #!/bin/bash
 cd /root/repo
-run() { echo "== $*"; env "$@" timeout 120 python tools/steptime.py 1.0 prof 2>&1 | grep -E "^\{|iter 3" | sed -e "s/'join_fast_//g"; }
-run GSQL_X=1
-run GSQL_JOIN_PROBE_PIPE=1 GSQL_JOIN_LOOKUP_MODE=2
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_operators_gpu.py -x -q -k "agg or Agg" 2>&1 | tail -5
+timeout 300 python tools/aggbench.py 1.0 2>&1 | tail -2
