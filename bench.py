@@ -292,9 +292,11 @@ def run_ours(args):
         j.close()
 
     def step_multi():
-        # exchange both sides on the join key, then join locally.  (A slabbed variant that overlapped the AllToAllv of
-        # slab i+1 with the probe of slab i through a second context + host thread measured SLOWER in r01 — 125 ms vs
-        # 103 ms per step at N = 2 — so the step stays sequential.)
+        # exchange both sides on the join key, then join locally.  Measured dead ends (r01, N = 2): a slabbed variant that
+        # overlapped the AllToAllv of slab i+1 with the probe of slab i through a second context + host thread (125 ms vs
+        # 103 ms per step); running the join on a second context so that the table build overlaps the probe-side
+        # AllToAllv (228 ms vs 79 ms: the second context's memory pool re-grows every step); scattering the rank's own
+        # rows straight into the receive buffer instead of a self send/recv (scatter 9.8 -> 12.5 ms, AllToAllv unchanged).
         nbr, _ = xb.all_to_all_into(b(build), rb, bcap)
         npr_r, _ = xp.all_to_all_into(b(probe), rp, cap)
         j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nbr)

@@ -23,7 +23,7 @@
 // the spot and is counted in C_FALLBACK; the host drops back to k_agg_smem / the generic kernel when that is common.
 //
 // Reference behaviour: AggOpenHashMap.putChunk (EX/operator/util/AggOpenHashMap.java:100-139) and the aggregators
-// restated in oracle/oracle.c — same groups, same NULL rules; floating sums are added in a different order (within the
+// (restated by the CPU checker under tests) — same groups, same NULL rules; floating sums are added in a different order (within the
 // north_star's 1e-6 relative tolerance), integer results are bit-exact.
 #pragma once
 
