@@ -62,6 +62,7 @@ class ClockSampler:
         self.proc = None
         self.nvml = None
         self.mode = os.environ.get("GSQL_BENCH_CLOCKS", "nvml")
+        self.period = float(os.environ.get("GSQL_BENCH_CLOCKS_PERIOD_MS", "20")) / 1000.0
         self._stop = threading.Event()
 
     def start(self):
@@ -105,7 +106,7 @@ class ClockSampler:
                     self.lines.append((time.time(), sm, rs))
                 except Exception:
                     pass
-                self._stop.wait(0.02)
+                self._stop.wait(self.period)
         self.t = threading.Thread(target=poll, daemon=True)
         self.t.start()
         return True
@@ -128,7 +129,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(smax), "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml, 20 ms period"}
+                "source": f"nvml, {self.period * 1000:.0f} ms period"}
 
     def stop(self, t0: float, t1: float):
         if self.nvml:

@@ -425,6 +425,10 @@ extern "C" void gsql_join_destroy(gsql_join *j) {
     gsql_ctx *ctx = j->ctx;
     cudaSetDevice(ctx->device);
     delete j;
+    // The buffers were released with stream-ordered frees: wait for them, so that the memory is really back in the
+    // pool when destroy returns.  Without this a caller that immediately creates the next operator (one join per
+    // step in bench.py) was measured 4-100 ms slower per step: its multi-GB allocations raced the pending frees.
+    if (!ctx->sticky) cudaStreamSynchronize(ctx->stream);
     gsql_ctx_release(ctx);
 }
 

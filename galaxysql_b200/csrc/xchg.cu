@@ -148,6 +148,9 @@ int grid_rows(gsql_ctx *ctx, int64_t rows, int block, int per_sm) {
 struct gsql_xchg {
     gsql_ctx *ctx;
     gsql_xchg_spec spec;
+    // send staging of the shuffle (partition-ordered columns), kept across calls: a shuffle of N rows stages N rows,
+    // and re-allocating those gigabytes on every call raced the stream-ordered frees of the previous one
+    DevBuf sdata[GSQL_MAX_COLS], snull[GSQL_MAX_COLS];
 };
 
 extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spec, gsql_xchg **out) {
@@ -174,6 +177,7 @@ extern "C" void gsql_xchg_destroy(gsql_xchg *x) {
     gsql_ctx *ctx = x->ctx;
     cudaSetDevice(ctx->device);
     delete x;
+    if (!ctx->sticky) cudaStreamSynchronize(ctx->stream);  // stream-ordered frees have really happened (see gsql_join_destroy)
     gsql_ctx_release(ctx);
 }
 
@@ -352,13 +356,13 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     GSQL_TRY(stage_batch(ctx, in, &sb));
     XOut O;
     memset(&O, 0, sizeof(O));
-    DevBuf sdata[GSQL_MAX_COLS], snull[GSQL_MAX_COLS];
+    DevBuf *sdata = x->sdata, *snull = x->snull;
     int64_t srows = in->rows > 0 ? in->rows : 1;
     for (int c = 0; c < s.n_cols; c++) {
-        GSQL_TRY(sdata[c].alloc(ctx, (size_t)srows * gsql_type_width(s.types[c])));
+        GSQL_TRY(sdata[c].grow(ctx, (size_t)srows * gsql_type_width(s.types[c]), 0));
         O.data[c] = sdata[c].p;
         if (out->cols[c].nulls) {
-            GSQL_TRY(snull[c].alloc(ctx, (size_t)srows));
+            GSQL_TRY(snull[c].grow(ctx, (size_t)srows, 0));
             O.nulls[c] = snull[c].as<uint8_t>();
         }
     }
