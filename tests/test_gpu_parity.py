@@ -240,6 +240,22 @@ def test_fast_join_small_batch_skips_partitioning(gu, monkeypatch, jt, fused_bui
     j.close()
 
 
+@pytest.mark.parametrize("variant", [{"GSQL_JOIN_TMA": "1"}, {"GSQL_JOIN_PROBE_PIPE": "1"}, {"GSQL_JOIN_PROBE_PIPE": "1", "GSQL_JOIN_LOOKUP_MODE": "2"},
+                                     {"GSQL_JOIN_LOOKUP_MODE": "0"}, {"GSQL_JOIN_LOOKUP_MODE": "2"}, {"GSQL_JOIN_SCATTER_PIPE": "0"}],
+                         ids=["tma", "pipe", "pipe+gather", "ld", "gather", "scatter-nopipe"])
+@pytest.mark.parametrize("jt", [orc.JOIN_INNER, orc.JOIN_LEFT, orc.JOIN_ANTI])
+def test_fast_join_opt_in_kernel_variants(gu, small_partitions, monkeypatch, variant, jt):
+    """The opt-in probe / scatter kernel variants kept for measurement (TMA-staged persistent probe, cp.async-prefetching
+    persistent probe, slot reads gathered through shared memory, plain slot loads, scatter without input double
+    buffering) must give the oracle's rows like the default kernels."""
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
+    outer, inner, kc = _unique_key_tables(40_000, 130_000, 60_000, np.int64, 2, 2, seed=5200 + jt)
+    spec = orc.JoinSpec(jt, [kc], [0], [orc.T_INT64])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    assert ku.rows_multiset(gu.gpu_hash_join(spec, outer, inner, mem="device")) == exp
+
+
 def test_fast_join_is_taken_and_falls_back(gu, small_partitions):
     from galaxysql_b200 import api, native as N
     outer, inner, kc = _unique_key_tables(40_000, 50_000, 60_000, np.int64, 2, 2, seed=77)
