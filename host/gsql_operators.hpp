@@ -302,11 +302,15 @@ class GpuParallelHashJoinExec : public Executor, public ConsumerExecutor {
 };
 
 struct Aggregator { int kind; std::vector<int> targetIndexes; int filterArg = -1; };
+// The Project / Filter directly under the HashAgg, fused into the aggregation kernels (VectorizedProjectExec.java:40-143,
+// VectorizedFilterExec): derived column i is addressed by the aggregators as input column inputTypes.size() + i.
+struct DerivedColumn { int kind; int a, b, c; };                      // GSQL_EXPR_MUL_1MINUS: a*(1-b); _1PLUS: a*(1-b)*(1+c)
+struct RowFilter { int col = -1; int op = GSQL_CMP_NONE; int64_t value = 0; };  // keeps rows with `col op value`; NULL never passes
 
 class GpuHashAggExec : public Executor, public ConsumerExecutor {
   public:
     GpuHashAggExec(const std::vector<int> &inputTypes, const std::vector<int> &groups, const std::vector<Aggregator> &aggs, int64_t expectedGroups,
-                   ExecutionContext *context)
+                   ExecutionContext *context, const std::vector<DerivedColumn> &derived = {}, const RowFilter &rowFilter = RowFilter())
         : ctx_(context), stage_(inputTypes) {
         gsql_agg_spec s;
         std::memset(&s, 0, sizeof(s));
@@ -322,7 +326,16 @@ class GpuHashAggExec : public Executor, public ConsumerExecutor {
             s.aggs[i].filter_arg = aggs[i].filterArg;
         }
         s.expected_groups = expectedGroups;
-        s.row_filter_col = -1;
+        s.n_derived = (int32_t)derived.size();
+        for (size_t i = 0; i < derived.size() && i < GSQL_MAX_DERIVED; i++) {
+            s.derived[i].kind = derived[i].kind;
+            s.derived[i].a = derived[i].a;
+            s.derived[i].b = derived[i].b;
+            s.derived[i].c = derived[i].c;
+        }
+        s.row_filter_col = rowFilter.col;
+        s.row_filter_op = rowFilter.op;
+        s.row_filter_value = rowFilter.value;
         ctx_->check(gsql_agg_create(ctx_->ctx, &s, &agg_));
         int32_t n = 0, types[GSQL_MAX_COLS];
         ctx_->check(gsql_agg_output_schema(agg_, &n, types));

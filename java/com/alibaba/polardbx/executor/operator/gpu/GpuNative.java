@@ -54,6 +54,15 @@ public final class GpuNative {
     public static native long aggCreate(long ctx, int[] inputTypes, int[] groups, int[] aggKinds, int[][] aggCols,
                                         int[] filterArgs, long expectedGroups);
 
+    /**
+     * Same, with the Project / Filter operators that sit directly under the HashAgg fused into the kernel
+     * (VectorizedProjectExec.java:40-143 / VectorizedFilterExec): derived columns {kind, a, b, c} are addressed by the
+     * aggregates as input column n_input_cols + i (kind 1: a*(1-b), kind 2: a*(1-b)*(1+c)); rowFilter = {col, op, value}
+     * keeps the rows with `col op value` (op: 1 <=, 2 <, 3 >=, 4 >, 5 =, 6 <>; NULL never passes), or null.
+     */
+    public static native long aggCreateFused(long ctx, int[] inputTypes, int[] groups, int[] aggKinds, int[][] aggCols,
+                                             int[] filterArgs, long expectedGroups, int[][] derived, long[] rowFilter);
+
     public static native void aggConsume(long agg, long staging);
 
     public static native long aggFinish(long agg);

@@ -159,6 +159,49 @@ JNIEXPORT jlong JNICALL Java_com_alibaba_polardbx_executor_operator_gpu_GpuNativ
     return (jlong)(intptr_t)j;
 }
 
+/* ---- aggregation with the Project / Filter under it fused in (gsql_agg_spec.derived / row_filter_*) ------------------ */
+JNIEXPORT jlong JNICALL Java_com_alibaba_polardbx_executor_operator_gpu_GpuNative_aggCreateFused(
+    JNIEnv *env, jclass c, jlong ctx, jintArray inputTypes, jintArray groups, jintArray aggKinds, jobjectArray aggCols, jintArray filterArgs,
+    jlong expectedGroups, jobjectArray derived, jlongArray rowFilter) {
+    gsql_agg_spec s;
+    memset(&s, 0, sizeof(s));
+    int32_t kinds[GSQL_MAX_AGGS], fargs[GSQL_MAX_AGGS], n;
+    fill_ints(env, inputTypes, s.input_types, &s.n_input_cols, GSQL_MAX_COLS);
+    fill_ints(env, groups, s.groups, &s.ngroups, GSQL_MAX_KEYS);
+    fill_ints(env, aggKinds, kinds, &s.naggs, GSQL_MAX_AGGS);
+    fill_ints(env, filterArgs, fargs, &n, GSQL_MAX_AGGS);
+    for (int i = 0; i < s.naggs; i++) {
+        jintArray cols = (jintArray)(*env)->GetObjectArrayElement(env, aggCols, i);
+        s.aggs[i].kind = kinds[i];
+        s.aggs[i].filter_arg = i < n ? fargs[i] : -1;
+        fill_ints(env, cols, s.aggs[i].cols, &s.aggs[i].ncols, 4);
+    }
+    s.expected_groups = expectedGroups;
+    s.n_derived = derived ? (*env)->GetArrayLength(env, derived) : 0;
+    if (s.n_derived > GSQL_MAX_DERIVED) s.n_derived = GSQL_MAX_DERIVED;
+    for (int i = 0; i < s.n_derived; i++) {
+        int32_t d[4] = {0, 0, 0, 0}, nd;
+        fill_ints(env, (jintArray)(*env)->GetObjectArrayElement(env, derived, i), d, &nd, 4);
+        s.derived[i].kind = d[0];
+        s.derived[i].a = d[1];
+        s.derived[i].b = d[2];
+        s.derived[i].c = d[3];
+    }
+    s.row_filter_col = -1;
+    s.row_filter_op = GSQL_CMP_NONE;
+    if (rowFilter) {
+        jlong f[3];
+        (*env)->GetLongArrayRegion(env, rowFilter, 0, 3, f);
+        s.row_filter_col = (int32_t)f[0];
+        s.row_filter_op = (int32_t)f[1];
+        s.row_filter_value = f[2];
+    }
+    gsql_agg *a = NULL;
+    int st = gsql_agg_create((gsql_ctx *)(intptr_t)ctx, &s, &a);
+    if (st != GSQL_OK) throw_status(env, (gsql_ctx *)(intptr_t)ctx, st);
+    return (jlong)(intptr_t)a;
+}
+
 /* The remaining entry points (joinBuildConsume / joinBuildFinish / joinProbe / joinUnmatchedBuild / agg* / xchg* /
  * stagingColumn / stagingNulls) follow the same pattern: as_batch(staging) in, gsql_* call, throw_status on error; for
  * outputs the shim calls the function with the staging's capacity, grows it on GSQL_E_CAPACITY and calls again. */
