@@ -418,17 +418,30 @@ def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
     batch = min(args.e2e_batch, npr)
     types = [N.T_INT64, N.T_INT32, N.T_INT32]
     tt = {N.T_INT64: torch.int64, N.T_INT32: torch.int32}
-    # host copies of the inputs (pinned) — made once, outside the timed region, like a caller that owns them
-    hbuild = [torch.empty(nb, dtype=c.dtype, pin_memory=True) for c in build]
+    # host copies of the inputs (pinned) — made once, outside the timed region, like a caller that owns them.  ~22 GB of
+    # pinned memory per rank: if any rank cannot get it, every rank skips the leg together (no half-entered collectives)
+    ok, hbuild, hprobe, hout = 1, None, None, None
+    try:
+        hbuild = [torch.empty(nb, dtype=c.dtype, pin_memory=True) for c in build]
+        hprobe = [torch.empty(npr, dtype=c.dtype, pin_memory=True) for c in probe]
+        hout = [torch.empty(batch, dtype=tt[t], pin_memory=True) for t in types + types]
+    except RuntimeError:
+        ok = 0
+    if world > 1:
+        okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        ok = int(okt.item())
+    if not ok:
+        del hbuild, hprobe, hout
+        return {"value": None, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "error": "pinned host buffers for the end-to-end leg could not be allocated on every rank"}
     for h, c in zip(hbuild, build):
         h.copy_(c)
-    hprobe = [torch.empty(npr, dtype=c.dtype, pin_memory=True) for c in probe]
     for i, (h, c) in enumerate(zip(hprobe, probe)):
         if i == 0 and world > 1:  # rank-local leg: map every probe key into this rank's share of the key space
             h.copy_((c // world) * world + rank)
         else:
             h.copy_(c)
-    hout = [torch.empty(batch, dtype=tt[t], pin_memory=True) for t in types + types]
     torch.cuda.synchronize()
 
     def view(tensors, lo, hi):
