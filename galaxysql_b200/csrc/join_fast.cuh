@@ -1,16 +1,22 @@
 // join_fast.cuh — radix-partitioned, L2-resident hash join for a single integer equi-key (the C2 / TPC-H shape).
 //
-// Why: on B200 a random 16-byte table read costs ~35 G reads/s when the table lives in HBM but ~230 G reads/s when
-// the touched slice of the table fits the 126 MB L2 (tools/microbench.cu, profiles/r01_microbench.txt).  So both
-// sides are range-partitioned on the TABLE SLOT (partition = slot / slots_per_partition = mulhi(fmix64(key), P)),
-// rows are packed into fixed-stride 8-byte-word rows {key, payload...}, and the probe walks partition after
-// partition so that the active slice of the table (<= ~32 MB) stays L2-resident while probe rows stream through
-// with evict-first loads/stores.  Every pass is a pure streaming pass over HBM:
-//     k_fj_hist     keys only          ->  [partition][block] histogram
-//     k_fj_scatter  all columns        ->  packed rows in partition order (shared-memory staged, full-sector writes)
-//     k_fj_insert   packed build rows  ->  open-addressing table of packed rows (key CAS, payload inline)
-//     k_fj_probe    packed probe rows  ->  output columns (one table read per probe row, warp-ballot compaction,
-//                                          one global cursor bump per 2048-row tile)
+// Why: on B200 a random 16-byte table read costs ~35 G reads/s when the table lives in HBM (each one drags a ~128-byte
+// fetch: 174 GB of DRAM traffic per 1 B probe rows, profiles/r01_ncu_summary.md prof_r01h) but ~230 G reads/s when the
+// touched slice of the table fits the 126 MB L2 (tools/microbench.cu, profiles/r01_microbench.txt).  So for tables
+// beyond L2 both sides are range-partitioned on the TABLE SLOT (slot = mulhi(key_hash, nslots), partition = the same
+// hash's high bits scaled to P, i.e. partition p owns the contiguous slot range p), rows are packed into fixed-stride
+// 8-byte-word rows {key, payload...}, and build and probe walk partition after partition so that the active 16 MB
+// slice of the table stays L2-resident while the rows stream through with evict-first loads/stores:
+//     k_fj_hist        keys only          ->  [partition][block] histogram
+//     k_fj_scatter     all columns        ->  packed rows in partition order (cp.async double-buffered column loads,
+//                                             shared-memory staged tile, 16-byte run writes)
+//     k_fj_build_part  packed build rows  ->  table; cooperative: EMPTY-fill a 16 MB partition group, grid barrier,
+//                                             CAS-insert into it while it is still dirty in L2
+//     k_fj_probe       packed probe rows  ->  output columns (one table read per probe row, warp-ballot compaction,
+//                                             one global cursor bump per 2048-row tile, full-line column flush)
+// Tables that fit L2 skip the partitioning: k_fj_table_init + k_fj_insert build them and k_fj_probe reads the probe rows
+// straight from the input columns.  k_fj_probe_pipe (persistent, cp.async row prefetch, ticketed tiles) and
+// k_fj_probe_tma (persistent, TMA-staged ring) are measurement variants kept behind environment switches.
 // The table holds whole build rows inline (stride = key + payload words), so a probe is ONE L2 access; duplicate
 // build keys, NULLs, composite/double keys, non-equi conditions and outer-build joins take the generic path in
 // join.cu (same results, two-pass sizing).
