@@ -18,6 +18,8 @@
 
 #include <algorithm>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace {
@@ -282,6 +284,67 @@ __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ Agg
             continue;
         }
         for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r);
+    }
+}
+
+// ---- optional pre-pass for tables beyond L2 (GSQL_AGG_PARTITION=1, not yet the default): the batch is reordered by
+// the high bits of the same hash that picks the table slot, so that k_agg_consume — which walks rows in index order —
+// touches one L2-sized slice of the slot array at a time; dense group ids are handed out in first-appearance order,
+// so the accumulators of a slice's groups are contiguous (and L2-resident) as well.  Same idea as the radix mode of
+// the join (join_fast.cuh): an HBM-resident slot read costs a ~128-byte fetch and an fp64 atomic on a line that misses
+// L2 runs at 21 G/s instead of 190 G/s (profiles/r01_microbench.txt).
+struct APart {
+    int32_t nparts, nblocks;
+    int64_t chunk;  // rows per block
+};
+struct APartOut {
+    void *data[GSQL_MAX_COLS];
+    uint8_t *nulls[GSQL_MAX_COLS];
+};
+
+__device__ __forceinline__ int agg_part_of(const AggParams &P, int64_t r, int nparts) {
+    int64_t kv[GSQL_MAX_KEYS];
+    bool kn[GSQL_MAX_KEYS];
+    unsigned long long d = load_group_key(P, r, kv, kn);
+    return (int)__umul64hi(gsql_fmix64(d), (uint64_t)nparts);  // slot = mulhi(fmix64(d), nslots): partition = slot range
+}
+
+__global__ void __launch_bounds__(256) k_agg_part_hist(const __grid_constant__ AggParams P, APart G, int64_t *__restrict__ hist) {
+    extern __shared__ unsigned int sh_part[];
+    for (int i = threadIdx.x; i < G.nparts; i += 256) sh_part[i] = 0;
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * G.chunk;
+    int64_t r1 = r0 + G.chunk < P.rows ? r0 + G.chunk : P.rows;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) atomicAdd(&sh_part[agg_part_of(P, r, G.nparts)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < G.nparts; i += 256) hist[(int64_t)i * G.nblocks + blockIdx.x] = sh_part[i];
+}
+
+__global__ void __launch_bounds__(256)
+    k_agg_part_scatter(const __grid_constant__ AggParams P, APart G, const int64_t *__restrict__ offs, const __grid_constant__ APartOut O) {
+    extern __shared__ unsigned long long cur_part[];
+    for (int i = threadIdx.x; i < G.nparts; i += 256) cur_part[i] = (unsigned long long)offs[(int64_t)i * G.nblocks + blockIdx.x];
+    __syncthreads();
+    int64_t r0 = (int64_t)blockIdx.x * G.chunk;
+    int64_t r1 = r0 + G.chunk < P.rows ? r0 + G.chunk : P.rows;
+    for (int64_t base = r0; base < r1; base += 256) {
+        int64_t r = base + threadIdx.x;
+        bool live = r < r1;
+        int p = live ? agg_part_of(P, r, G.nparts) : -1;
+        unsigned peers = __match_any_sync(0xffffffffu, p);  // one shared-memory atomic per distinct partition per warp
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(peers) - 1;
+        unsigned long long basepos = 0;
+        if (live && lane == leader) basepos = atomicAdd(&cur_part[p], (unsigned long long)__popc(peers));
+        basepos = __shfl_sync(0xffffffffu, basepos, leader);
+        if (!live) continue;
+        int64_t pos = (int64_t)basepos + __popc(peers & ((1u << lane) - 1));
+        for (int c = 0; c < P.in.n; c++) {
+            const DCol &col = P.in.c[c];
+            if (col.type == GSQL_T_INT32) reinterpret_cast<int32_t *>(O.data[c])[pos] = reinterpret_cast<const int32_t *>(col.data)[r];
+            else reinterpret_cast<int64_t *>(O.data[c])[pos] = reinterpret_cast<const int64_t *>(col.data)[r];
+            if (O.nulls[c]) O.nulls[c][pos] = col.nulls[r];
+        }
     }
 }
 
@@ -580,6 +643,7 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     }
     cudaSetDevice(ctx->device);
     agg_fast_plan(&a->fast, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    if (s.expected_groups > (1 << 16)) a->fast.enabled = false;  // the planner expects far more groups than warp tables hold
     agg_lane_check(&a->lane, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
     if ((getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) || (getenv("GSQL_AGG_NO_LANE") && atoi(getenv("GSQL_AGG_NO_LANE"))))
@@ -620,6 +684,57 @@ static gsql_status agg_read_counters(gsql_agg *a, unsigned long long *h) {
     return GSQL_OK;
 }
 
+// Reorders the staged batch by table-slot range (see k_agg_part_hist).  `sb` is rewritten to point at the reordered
+// columns, which live in `bufs` until the caller returns.
+static gsql_status agg_partition_batch(gsql_agg *a, StagedBatch *sb, int nparts, DevBuf *bufs, DevBuf *nbufs) {
+    gsql_ctx *ctx = a->ctx;
+    AggParams P;
+    agg_fill_params(a, sb, &P);
+    P.row0 = 0;
+    P.rows = sb->rows;
+    APart G;
+    int nblocks = grid_rows(ctx, sb->rows, 4096, 8);
+    G.chunk = div_up(div_up(sb->rows, nblocks), 256) * 256;
+    nblocks = (int)div_up(sb->rows, G.chunk);
+    if (nblocks < 1) nblocks = 1;
+    G.nblocks = nblocks;
+    G.nparts = nparts;
+    int64_t nh = (int64_t)nparts * nblocks;
+    DevBuf hist, offs, tmp;
+    GSQL_TRY(hist.alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_TRY(offs.alloc(ctx, (size_t)(nh + 1) * 8));
+    GSQL_CUDA(ctx, cudaMemsetAsync((char *)hist.p + nh * 8, 0, 8, ctx->stream));
+    {
+        KernelScope ks(ctx, "agg_part_hist");
+        k_agg_part_hist<<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    size_t tb = 0;
+    GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist.as<int64_t>(), offs.as<int64_t>(), nh + 1, ctx->stream));
+    GSQL_TRY(tmp.alloc(ctx, tb));
+    GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist.as<int64_t>(), offs.as<int64_t>(), nh + 1, ctx->stream));
+    APartOut O;
+    memset(&O, 0, sizeof(O));
+    for (int c = 0; c < sb->ncols; c++) {
+        GSQL_TRY(bufs[c].alloc(ctx, (size_t)sb->rows * gsql_type_width(sb->cols[c].type)));
+        O.data[c] = bufs[c].p;
+        if (sb->cols[c].nulls) {
+            GSQL_TRY(nbufs[c].alloc(ctx, (size_t)sb->rows));
+            O.nulls[c] = nbufs[c].as<uint8_t>();
+        }
+    }
+    {
+        KernelScope ks(ctx, "agg_part_scatter");
+        k_agg_part_scatter<<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O);
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    for (int c = 0; c < sb->ncols; c++) {
+        sb->cols[c].data = O.data[c];
+        sb->cols[c].nulls = O.nulls[c];
+    }
+    return GSQL_OK;
+}
+
 extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     if (!a) return GSQL_E_INVALID;
     gsql_ctx *ctx = a->ctx;
@@ -631,6 +746,22 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     StagedBatch sb;
     GSQL_TRY(stage_batch(ctx, batch, &sb));
     GSQL_TRY(a->overflow.grow(ctx, (size_t)batch->rows * 8, 0));
+    // opt-in (GSQL_AGG_PARTITION=1): a large batch headed for the generic kernel against a table beyond L2 is first
+    // reordered by table-slot range
+    DevBuf part_data[GSQL_MAX_COLS], part_nulls[GSQL_MAX_COLS];
+    {
+        static const bool part_on = getenv("GSQL_AGG_PARTITION") && atoi(getenv("GSQL_AGG_PARTITION"));
+        const bool generic = !(a->lane.shape_ok && a->lane.enabled) && !(a->fast.eligible && a->fast.enabled);
+        int64_t per_group = 2 * (int64_t)sizeof(ASlot) + (int64_t)a->nkeys * 9 + (int64_t)a->naggs * 9;
+        int64_t table_bytes = (a->gcap + a->slack) * per_group;
+        int64_t min_rows = getenv("GSQL_AGG_PARTITION_MIN_ROWS") ? atoll(getenv("GSQL_AGG_PARTITION_MIN_ROWS")) : (1ll << 22);
+        int64_t slice = getenv("GSQL_AGG_PARTITION_BYTES") ? atoll(getenv("GSQL_AGG_PARTITION_BYTES")) : (16ll << 20);
+        if (part_on && generic && a->nkeys > 0 && batch->rows >= min_rows && table_bytes > 4 * slice) {
+            int64_t nparts = div_up(table_bytes, slice);
+            if (nparts > 4096) nparts = 4096;
+            GSQL_TRY(agg_partition_batch(a, &sb, (int)nparts, part_data, part_nulls));
+        }
+    }
     AggParams P;
     agg_fill_params(a, &sb, &P);
     P.row0 = 0;

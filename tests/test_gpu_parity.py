@@ -4,6 +4,8 @@ Bars (north_star): integer / COUNT / key / payload columns bit-exact, floating S
 results compared as order-insensitive row multisets like the reference's own tests (BaseExecTest.java:78-103).
 Run on the B200 box with `pytest -m gpu`.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -473,6 +475,24 @@ def test_agg_lane_kernel_is_taken_for_q1_shape(gu):
     oaggs = [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_AVG, [3]),
              orc.AggCall(orc.AGG_COUNT_STAR)]
     gu.approx_rows_equal(got, orc.hash_agg(cols, [0, 1], oaggs, 8), float_cols=[2, 3, 4, 5], key_cols=[0, 1], rtol=RTOL)
+
+
+@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="opt-in pre-pass (GSQL_AGG_PARTITION=1) written at the end of r01 without GPU time left; enable to validate")
+def test_agg_partition_prepass_experimental(gu, monkeypatch):
+    """High-cardinality group-by with the batch first reordered by table-slot range (k_agg_part_hist / _scatter)."""
+    monkeypatch.setenv("GSQL_AGG_PARTITION", "1")
+    monkeypatch.setenv("GSQL_AGG_PARTITION_MIN_ROWS", "1000")
+    monkeypatch.setenv("GSQL_AGG_PARTITION_BYTES", str(1 << 20))
+    n = 600_000
+    k = (ku.rand_u64(n, 61) % np.uint64(200_000)).astype(np.int64) * 7919 - 5
+    v = (ku.rand_u64(n, 62) % np.uint64(1000)).astype(np.float64)
+    w = (ku.rand_u64(n, 63) % np.uint64(1000)).astype(np.int32)
+    cols = [ku.with_nulls(k, 0.01, 64), ku.with_nulls(v, 0.02, 65), (w, None)]
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_MAX, [2]), orc.AggCall(orc.AGG_AVG, [1])]
+    exp = orc.hash_agg(cols, [0], aggs, 300_000)
+    got = gu.gpu_hash_agg(cols, [0], aggs, 300_000, mem="device", batches=2)
+    gu.approx_rows_equal(got, exp, float_cols=[2, 4], key_cols=[0], rtol=RTOL)
 
 
 def test_agg_smem_path_adapts_to_high_cardinality(gu):
