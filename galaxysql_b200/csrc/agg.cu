@@ -750,7 +750,7 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     // reordered by table-slot range
     DevBuf part_data[GSQL_MAX_COLS], part_nulls[GSQL_MAX_COLS];
     {
-        static const bool part_on = getenv("GSQL_AGG_PARTITION") && atoi(getenv("GSQL_AGG_PARTITION"));
+        const bool part_on = getenv("GSQL_AGG_PARTITION") && atoi(getenv("GSQL_AGG_PARTITION"));
         const bool generic = !(a->lane.shape_ok && a->lane.enabled) && !(a->fast.eligible && a->fast.enabled);
         int64_t per_group = 2 * (int64_t)sizeof(ASlot) + (int64_t)a->nkeys * 9 + (int64_t)a->naggs * 9;
         int64_t table_bytes = (a->gcap + a->slack) * per_group;

@@ -335,6 +335,165 @@ extern "C" gsql_status gsql_comm_destroy(gsql_ctx *ctx) {
     return GSQL_OK;
 }
 
+// ---- opt-in slabbed shuffle (GSQL_XCHG_SLABS=S > 1; written at the end of r01, compiled, not yet run on GPUs) -----------
+// The sequential path partitions the whole batch, then sends it: the scatter pass (HBM-bound) and the AllToAllv
+// (NVLink-bound) never overlap.  Here the batch is cut into S row slabs.  All S histograms run first (keys only), one
+// count exchange covers every (slab, destination) pair, and then slab i+1 is scattered on the context stream while the
+// segments of slab i travel on the stripe streams.  Receive layout is the sequential path's: per source rank contiguous
+// (its slabs one after the other).
+static void fill_xparams(gsql_xchg *x, const StagedBatch &sb, int64_t row0, int64_t rows, XParams *Pp) {
+    const gsql_xchg_spec &s = x->spec;
+    XParams &P = *Pp;
+    memset(&P, 0, sizeof(P));
+    P.in.n = sb.ncols;
+    for (int i = 0; i < sb.ncols; i++) {
+        P.in.c[i] = sb.cols[i];
+        P.in.c[i].data = (const char *)sb.cols[i].data + (size_t)row0 * gsql_type_width(sb.cols[i].type);
+        if (sb.cols[i].nulls) P.in.c[i].nulls = sb.cols[i].nulls + row0;
+    }
+    P.keys.n = s.n_channels;
+    for (int i = 0; i < s.n_channels; i++) {
+        P.keys.c[i] = P.in.c[s.channels[i]];
+        P.keys.utype[i] = s.key_types[i];
+    }
+    P.nparts = s.nparts;
+    P.pow2 = (s.nparts & -s.nparts) == s.nparts;
+    P.rows = rows;
+    int nblocks = grid_rows(x->ctx, rows, 4096, 8);
+    P.chunk = div_up(rows > 0 ? rows : 1, nblocks);
+    P.chunk = div_up(P.chunk, XBLOCK) * XBLOCK;
+    nblocks = (int)div_up(rows, P.chunk);
+    if (nblocks < 1) nblocks = 1;
+    P.nblocks = nblocks;
+}
+
+static gsql_status all_to_all_slabbed(gsql_xchg *x, const StagedBatch &sb, gsql_batch *out, int64_t out_capacity, int64_t *out_rows,
+                                      int64_t *recv_counts, int S) {
+    gsql_ctx *ctx = x->ctx;
+    const gsql_xchg_spec &s = x->spec;
+    NcclApi *api = nccl_api();
+    const int R = ctx->nranks, K = ctx->n_extra;  // all NCCL traffic on the stripe streams: the context stream keeps scattering
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const int64_t n = sb.rows;
+    const int64_t SR = div_up(div_up(n > 0 ? n : 1, S), XBLOCK) * XBLOCK;  // rows per slab (the last ones may be short or empty)
+    DevBuf *sdata = x->sdata, *snull = x->snull;
+    for (int c = 0; c < s.n_cols; c++) {
+        GSQL_TRY(sdata[c].grow(ctx, (size_t)(n > 0 ? n : 1) * gsql_type_width(s.types[c]), 0));
+        if (out->cols[c].nulls) GSQL_TRY(snull[c].grow(ctx, (size_t)(n > 0 ? n : 1), 0));
+    }
+    // ---- 1. histograms + scans of every slab
+    std::vector<XParams> P((size_t)S);
+    std::vector<DevBuf> hist((size_t)S), offs((size_t)S);
+    std::vector<int64_t> rows_of((size_t)S, 0);
+    DevBuf tmp;
+    size_t tmp_bytes = 0;
+    for (int i = 0; i < S; i++) {
+        const int64_t lo = (int64_t)i * SR;
+        rows_of[(size_t)i] = lo < n ? (n - lo < SR ? n - lo : SR) : 0;
+        fill_xparams(x, sb, lo < n ? lo : 0, rows_of[(size_t)i], &P[(size_t)i]);
+        const int64_t nh = (int64_t)s.nparts * P[(size_t)i].nblocks;
+        GSQL_TRY(hist[(size_t)i].alloc(ctx, (size_t)(nh + 1) * 8));
+        GSQL_TRY(offs[(size_t)i].alloc(ctx, (size_t)(nh + 1) * 8));
+        GSQL_CUDA(ctx, cudaMemsetAsync(hist[(size_t)i].p, 0, (size_t)(nh + 1) * 8, ctx->stream));
+        size_t tb = 0;
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist[(size_t)i].as<int64_t>(), offs[(size_t)i].as<int64_t>(), nh + 1, ctx->stream));
+        if (tb > tmp_bytes) tmp_bytes = tb;
+    }
+    GSQL_TRY(tmp.alloc(ctx, tmp_bytes));
+    for (int i = 0; i < S; i++) {
+        const int64_t nh = (int64_t)s.nparts * P[(size_t)i].nblocks;
+        if (rows_of[(size_t)i] > 0) {
+            KernelScope ks(ctx, "xchg_hist");
+            k_xchg_hist<<<P[(size_t)i].nblocks, XBLOCK, s.nparts * sizeof(unsigned int), ctx->stream>>>(P[(size_t)i], hist[(size_t)i].as<int64_t>());
+        }
+        size_t tb = tmp_bytes;
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist[(size_t)i].as<int64_t>(), offs[(size_t)i].as<int64_t>(), nh + 1, ctx->stream));
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    // ---- 2. counts[slab][dst] to the host, one AllGather of S x R counts
+    std::vector<int64_t> starts((size_t)S * (R + 1), 0), counts((size_t)S * R, 0);
+    for (int i = 0; i < S; i++)
+        GSQL_CUDA(ctx, cudaMemcpy2DAsync(&starts[(size_t)i * (R + 1)], 8, offs[(size_t)i].p, (size_t)P[(size_t)i].nblocks * 8, 8, (size_t)R,
+                                         cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < S; i++) {
+        starts[(size_t)i * (R + 1) + R] = rows_of[(size_t)i];
+        for (int d = 0; d < R; d++) counts[(size_t)i * R + d] = starts[(size_t)i * (R + 1) + d + 1] - starts[(size_t)i * (R + 1) + d];
+    }
+    DevBuf d_counts, d_matrix;
+    GSQL_TRY(d_counts.alloc(ctx, (size_t)S * R * 8));
+    GSQL_TRY(d_matrix.alloc(ctx, (size_t)R * S * R * 8));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(d_counts.p, counts.data(), (size_t)S * R * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GSQL_NCCL(ctx, api->AllGather(d_counts.p, d_matrix.p, (size_t)S * R, ncclInt64, comm, ctx->stream));
+    std::vector<int64_t> M((size_t)R * S * R);  // M[src][slab][dst]
+    GSQL_CUDA(ctx, cudaMemcpyAsync(M.data(), d_matrix.p, M.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int me = ctx->rank;
+    auto m_at = [&](int src, int slab, int dst) -> int64_t { return M[((size_t)src * S + slab) * R + dst]; };
+    std::vector<int64_t> rbase((size_t)R, 0);  // first receive row of each source
+    int64_t total = 0;
+    for (int src = 0; src < R; src++) {
+        rbase[(size_t)src] = total;
+        int64_t from = 0;
+        for (int i = 0; i < S; i++) from += m_at(src, i, me);
+        if (recv_counts) recv_counts[src] = from;
+        total += from;
+    }
+    *out_rows = total;
+    if (total > out_capacity) return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
+    // ---- 3. scatter slab i (context stream), then its segments leave on the stripe streams while slab i+1 is scattered
+    KernelScope ks(ctx, "xchg_alltoall");
+    std::vector<int64_t> rdone((size_t)R, 0);  // rows already received from each source (earlier slabs)
+    for (int i = 0; i < S; i++) {
+        const int64_t lo = (int64_t)i * SR;
+        if (rows_of[(size_t)i] > 0) {
+            XOut O;
+            memset(&O, 0, sizeof(O));
+            for (int c = 0; c < s.n_cols; c++) {
+                O.data[c] = (char *)sdata[c].p + (size_t)lo * gsql_type_width(s.types[c]);
+                if (out->cols[c].nulls) O.nulls[c] = snull[c].as<uint8_t>() + lo;
+            }
+            k_xchg_scatter<<<P[(size_t)i].nblocks, XBLOCK, s.nparts * sizeof(unsigned long long), ctx->stream>>>(P[(size_t)i], offs[(size_t)i].as<int64_t>(), O);
+            GSQL_CUDA(ctx, cudaGetLastError());
+        }
+        cudaEvent_t ready;
+        GSQL_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        GSQL_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
+        for (int k = 0; k < K; k++) {
+            ncclComm_t cm = (ncclComm_t)ctx->nccl_extra[k];
+            cudaStream_t st = ctx->xstreams[k];
+            GSQL_CUDA(ctx, cudaStreamWaitEvent(st, ready, 0));
+            GSQL_NCCL(ctx, api->GroupStart());
+            for (int c = 0; c < s.n_cols; c++) {
+                const size_t w = (size_t)gsql_type_width(s.types[c]);
+                for (int peer = 0; peer < R; peer++) {
+                    const int64_t ns = counts[(size_t)i * R + peer], nr = m_at(peer, i, me);
+                    const int64_t soff = lo + starts[(size_t)i * (R + 1) + peer], roff = rbase[(size_t)peer] + rdone[(size_t)peer];
+                    const int64_t s0 = ns * k / K, s1 = ns * (k + 1) / K, r0 = nr * k / K, r1 = nr * (k + 1) / K;
+                    if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)sdata[c].p + (size_t)(soff + s0) * w, (size_t)(s1 - s0) * w, ncclInt8, peer, cm, st));
+                    if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].data + (size_t)(roff + r0) * w, (size_t)(r1 - r0) * w, ncclInt8, peer, cm, st));
+                    if (out->cols[c].nulls) {
+                        if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)snull[c].p + soff + s0, (size_t)(s1 - s0), ncclInt8, peer, cm, st));
+                        if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].nulls + roff + r0, (size_t)(r1 - r0), ncclInt8, peer, cm, st));
+                    }
+                }
+            }
+            GSQL_NCCL(ctx, api->GroupEnd());
+        }
+        GSQL_CUDA(ctx, cudaEventDestroy(ready));
+        for (int peer = 0; peer < R; peer++) rdone[(size_t)peer] += m_at(peer, i, me);
+    }
+    for (int k = 0; k < K; k++) {  // join the stripes back into the context stream
+        cudaEvent_t done;
+        GSQL_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+        GSQL_CUDA(ctx, cudaEventRecord(done, ctx->xstreams[k]));
+        GSQL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done, 0));
+        GSQL_CUDA(ctx, cudaEventDestroy(done));
+    }
+    out->rows = total;
+    return GSQL_OK;
+}
+
 extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t out_capacity,
                                             int64_t *out_rows, int64_t *recv_counts) {
     if (!x || !in || !out || !out_rows) return GSQL_E_INVALID;
@@ -354,6 +513,10 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     // ---- 1. partition into contiguous per-destination segments
     StagedBatch sb;
     GSQL_TRY(stage_batch(ctx, in, &sb));
+    {
+        const int slabs = getenv("GSQL_XCHG_SLABS") ? atoi(getenv("GSQL_XCHG_SLABS")) : 1;  // every rank must use the same value
+        if (slabs > 1 && slabs <= 64 && ctx->n_extra > 0) return all_to_all_slabbed(x, sb, out, out_capacity, out_rows, recv_counts, slabs);
+    }
     XOut O;
     memset(&O, 0, sizeof(O));
     DevBuf *sdata = x->sdata, *snull = x->snull;

@@ -385,6 +385,23 @@ def test_all_to_all_single_rank(gu):
     c.lib.gsql_comm_destroy(c.ptr)
 
 
+@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="opt-in slabbed AllToAllv (GSQL_XCHG_SLABS) written at the end of r01 without GPU time left; enable to validate")
+def test_all_to_all_single_rank_slabbed_experimental(gu, monkeypatch):
+    """Same as above through the slabbed pipeline: 3 slabs (the last one short), NULL masks, per-source contiguous output."""
+    from galaxysql_b200 import api
+    monkeypatch.setenv("GSQL_XCHG_SLABS", "3")
+    c = gu.ctx()
+    api.comm_init(c, 1, 0, api.comm_unique_id())
+    n = 50_001
+    cols = [((ku.rand_u64(n, 1) % np.uint64(999)).astype(np.int64), None), ku.with_nulls(np.arange(n, dtype=np.int32), 0.1, 9)]
+    x = api.Exchange(c, [1, 0], [0], 1)
+    out, recv = x.all_to_all(gu.to_device(cols), capacity=n)
+    assert recv.tolist() == [n]
+    assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
+    c.lib.gsql_comm_destroy(c.ptr)
+
+
 # ------------------------------------------------------------------------------------------------ low-cardinality / fused Q1 shape
 def test_agg_q1_shape_fused_project_filter(gu):
     """TPC-H Q1 shape: 2 INT keys (3 x 2 values), fused derived columns price*(1-disc), price*(1-disc)*(1+tax) and the
