@@ -781,12 +781,21 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
             int64_t steps = div_up(P.rows, 32 * LA_R * LA_WARPS);
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count, steps);
             if (grid < 1) grid = 1;
-            static int attr_smem = 0;
-            if (LP.total > attr_smem) {
-                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
-                attr_smem = LP.total;
+            if (LP.f64_shape) {  // opt-in specialisation (GSQL_AGG_LANE_F64=1)
+                static int attr_smem_f64 = 0;
+                if (LP.total > attr_smem_f64) {
+                    GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
+                    attr_smem_f64 = LP.total;
+                }
+                k_agg_lane_f64<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
+            } else {
+                static int attr_smem = 0;
+                if (LP.total > attr_smem) {
+                    GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
+                    attr_smem = LP.total;
+                }
+                k_agg_lane<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
             }
-            k_agg_lane<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
         } else if (use_smem) {
             KernelScope ks(ctx, "agg_smem");
             int64_t warps = div_up(P.rows, 32);

@@ -512,6 +512,41 @@ def test_agg_partition_prepass_experimental(gu, monkeypatch):
     gu.approx_rows_equal(got, exp, float_cols=[2, 4], key_cols=[0], rtol=RTOL)
 
 
+@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
+                    reason="opt-in k_agg_lane_f64 (GSQL_AGG_LANE_F64=1) written at the end of r01 without GPU time left; enable to validate")
+@pytest.mark.parametrize("ngroups", [1, 6, 40])
+def test_agg_lane_f64_variant_experimental(gu, monkeypatch, ngroups):
+    """Branch-free fp64-only lane kernel: Q1 shape with fused derived columns and the row filter, no NULL buffers; 40 groups
+    overflow the warp dictionaries (in-kernel generic fallback)."""
+    from galaxysql_b200 import api, native as N
+    monkeypatch.setenv("GSQL_AGG_LANE_F64", "1")
+    n = 700_001
+    flag = (ku.rand_u64(n, 71) % np.uint64(ngroups)).astype(np.int32) - 3
+    status = (ku.rand_u64(n, 72) % np.uint64(2)).astype(np.int32)
+    qty = ((ku.rand_u64(n, 73) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
+    price = ((ku.rand_u64(n, 74) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    disc = (ku.rand_u64(n, 75) % np.uint64(11)).astype(np.float64) / 100.0
+    tax = (ku.rand_u64(n, 76) % np.uint64(9)).astype(np.float64) / 100.0
+    ship = ((ku.rand_u64(n, 77) % np.uint64(2526)) + np.uint64(8036)).astype(np.int32)
+    cutoff = 10471
+    cols = [(flag, None), (status, None), (qty, None), (price, None), (disc, None), (tax, None), (ship, None)]
+    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [7]), (N.AGG_SUM, [8]), (N.AGG_AVG, [2]), (N.AGG_AVG, [3]),
+            (N.AGG_AVG, [4]), (N.AGG_COUNT_STAR, [])]
+    a = api.HashAgg(gu.ctx(), [0, 0, 2, 2, 2, 2, 0], [0, 1], aggs, 64,
+                    derived=[(N.EXPR_MUL_1MINUS, 3, 4, 0), (N.EXPR_MUL_1MINUS_1PLUS, 3, 4, 5)], row_filter=(6, N.CMP_LE, cutoff))
+    for lo, hi in ((0, 300_000), (300_000, n)):
+        a.consume(gu.to_device([(d[lo:hi], None) for d, _ in cols]))
+    got = gu.to_numpy(a.result(N.MEM_DEVICE))
+    a.close()
+    m = ship <= cutoff
+    e1 = price * (1.0 - disc)
+    e2 = e1 * (1.0 + tax)
+    ocols = [(flag[m], None), (status[m], None), (qty[m], None), (price[m], None), (disc[m], None), (e1[m], None), (e2[m], None)]
+    oaggs = [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_SUM, [5]), orc.AggCall(orc.AGG_SUM, [6]),
+             orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_AVG, [3]), orc.AggCall(orc.AGG_AVG, [4]), orc.AggCall(orc.AGG_COUNT_STAR)]
+    gu.approx_rows_equal(got, orc.hash_agg(ocols, [0, 1], oaggs, 64), float_cols=[2, 3, 4, 5, 6, 7, 8], key_cols=[0, 1], rtol=RTOL)
+
+
 def test_agg_smem_path_adapts_to_high_cardinality(gu):
     """The shared-memory path must stay correct when the key set does not fit the CTA tables (rows bypass them)."""
     n = 400_000
