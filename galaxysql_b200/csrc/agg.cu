@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ Agg
     }
 }
 
-// ---- optional pre-pass for tables beyond L2 (GSQL_AGG_PARTITION=1, not yet the default): the batch is reordered by
+// ---- optional pre-pass for tables beyond L2 (GSQL_AGG_PARTITION=1; parity-checked on B200, not measured yet, hence not the default): the batch is reordered by
 // the high bits of the same hash that picks the table slot, so that k_agg_consume — which walks rows in index order —
 // touches one L2-sized slice of the slot array at a time; dense group ids are handed out in first-appearance order,
 // so the accumulators of a slice's groups are contiguous (and L2-resident) as well.  Same idea as the radix mode of

@@ -335,7 +335,7 @@ extern "C" gsql_status gsql_comm_destroy(gsql_ctx *ctx) {
     return GSQL_OK;
 }
 
-// ---- opt-in slabbed shuffle (GSQL_XCHG_SLABS=S > 1; written at the end of r01, compiled, not yet run on GPUs) -----------
+// ---- opt-in slabbed shuffle (GSQL_XCHG_SLABS=S > 1; parity-checked on one B200 rank at the end of r01, performance not measured yet) -----------
 // The sequential path partitions the whole batch, then sends it: the scatter pass (HBM-bound) and the AllToAllv
 // (NVLink-bound) never overlap.  Here the batch is cut into S row slabs.  All S histograms run first (keys only), one
 // count exchange covers every (slab, destination) pair, and then slab i+1 is scattered on the context stream while the

@@ -385,9 +385,7 @@ def test_all_to_all_single_rank(gu):
     c.lib.gsql_comm_destroy(c.ptr)
 
 
-@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="opt-in slabbed AllToAllv (GSQL_XCHG_SLABS) written at the end of r01 without GPU time left; enable to validate")
-def test_all_to_all_single_rank_slabbed_experimental(gu, monkeypatch):
+def test_all_to_all_single_rank_slabbed_opt_in(gu, monkeypatch):
     """Same as above through the slabbed pipeline: 3 slabs (the last one short), NULL masks, per-source contiguous output."""
     from galaxysql_b200 import api
     monkeypatch.setenv("GSQL_XCHG_SLABS", "3")
@@ -494,9 +492,7 @@ def test_agg_lane_kernel_is_taken_for_q1_shape(gu):
     gu.approx_rows_equal(got, orc.hash_agg(cols, [0, 1], oaggs, 8), float_cols=[2, 3, 4, 5], key_cols=[0, 1], rtol=RTOL)
 
 
-@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="opt-in pre-pass (GSQL_AGG_PARTITION=1) written at the end of r01 without GPU time left; enable to validate")
-def test_agg_partition_prepass_experimental(gu, monkeypatch):
+def test_agg_partition_prepass_opt_in(gu, monkeypatch):
     """High-cardinality group-by with the batch first reordered by table-slot range (k_agg_part_hist / _scatter)."""
     monkeypatch.setenv("GSQL_AGG_PARTITION", "1")
     monkeypatch.setenv("GSQL_AGG_PARTITION_MIN_ROWS", "1000")
@@ -512,10 +508,8 @@ def test_agg_partition_prepass_experimental(gu, monkeypatch):
     gu.approx_rows_equal(got, exp, float_cols=[2, 4], key_cols=[0], rtol=RTOL)
 
 
-@pytest.mark.skipif(os.environ.get("GSQL_TEST_EXPERIMENTAL", "0") == "0",
-                    reason="opt-in k_agg_lane_f64 (GSQL_AGG_LANE_F64=1) written at the end of r01 without GPU time left; enable to validate")
 @pytest.mark.parametrize("ngroups", [1, 6, 40])
-def test_agg_lane_f64_variant_experimental(gu, monkeypatch, ngroups):
+def test_agg_lane_f64_variant_opt_in(gu, monkeypatch, ngroups):
     """Branch-free fp64-only lane kernel: Q1 shape with fused derived columns and the row filter, no NULL buffers; 40 groups
     overflow the warp dictionaries (in-kernel generic fallback)."""
     from galaxysql_b200 import api, native as N
