@@ -370,8 +370,9 @@ def test_partition_exchange_vs_oracle(gu, nparts, mem):
         off += exp_counts[p]
 
 
-def test_all_to_all_single_rank(gu):
-    """The NCCL path with a 1-rank communicator: partition + self send/recv must return every row."""
+def test_all_to_all_single_rank(gu, monkeypatch):
+    """The NCCL path with a 1-rank communicator: partition + self send/recv must return every row — through the
+    sequential path and through the opt-in slabbed pipeline (GSQL_XCHG_SLABS: 3 slabs, the last one short, NULL masks)."""
     import torch
     from galaxysql_b200 import api
     c = gu.ctx()
@@ -382,21 +383,13 @@ def test_all_to_all_single_rank(gu):
     out, recv = x.all_to_all(gu.to_device(cols), capacity=n)
     assert recv.tolist() == [n]
     assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
-    c.lib.gsql_comm_destroy(c.ptr)
-
-
-def test_all_to_all_single_rank_slabbed_opt_in(gu, monkeypatch):
-    """Same as above through the slabbed pipeline: 3 slabs (the last one short), NULL masks, per-source contiguous output."""
-    from galaxysql_b200 import api
     monkeypatch.setenv("GSQL_XCHG_SLABS", "3")
-    c = gu.ctx()
-    api.comm_init(c, 1, 0, api.comm_unique_id())
-    n = 50_001
-    cols = [((ku.rand_u64(n, 1) % np.uint64(999)).astype(np.int64), None), ku.with_nulls(np.arange(n, dtype=np.int32), 0.1, 9)]
-    x = api.Exchange(c, [1, 0], [0], 1)
-    out, recv = x.all_to_all(gu.to_device(cols), capacity=n)
-    assert recv.tolist() == [n]
-    assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
+    n2 = 50_001
+    cols2 = [((ku.rand_u64(n2, 2) % np.uint64(999)).astype(np.int64), None), ku.with_nulls(np.arange(n2, dtype=np.int32), 0.1, 9)]
+    out2, recv2 = x.all_to_all(gu.to_device(cols2), capacity=n2)
+    assert recv2.tolist() == [n2]
+    assert ku.rows_multiset(gu.to_numpy(out2)) == ku.rows_multiset(cols2)
+    monkeypatch.delenv("GSQL_XCHG_SLABS")
     c.lib.gsql_comm_destroy(c.ptr)
 
 
