@@ -633,7 +633,9 @@ static gsql_status fast_build(gsql_join *j) {
     KeySet bkeys;
     fill_build_cols(j, &build, &bkeys);
     DevBuf packed, part_offs;
-    const bool fused = F.P > 1 && env_i64("GSQL_JOIN_BUILD_FUSED", 1);
+    int coop = 0;  // the fused build needs a cooperative launch (grid barrier); every sm_100 part has it, older stacks may not
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) != cudaSuccess) coop = 0;
+    const bool fused = F.P > 1 && coop && env_i64("GSQL_JOIN_BUILD_FUSED", 1);
     if (!fused) {
         KernelScope ks(ctx, "join_fast_table_init");
         int grid = grid_rows(ctx, (int64_t)F.nslots, 256, 8);
