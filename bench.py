@@ -45,6 +45,10 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary group-by measurement (Q1 shape)")
     ap.add_argument("--e2e-batch", type=int, default=125_000_000, help="probe rows per host batch in the e2e leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "q3", "c5"],
+                    help="c2 (default, the contract line): BASELINE config 2 join; q3 / c5: BASELINE configs 4 / 5 pipelines")
+    ap.add_argument("--slabs", type=int, default=int(os.environ.get("GSQL_BENCH_SLABS", "4")),
+                    help="probe-side slabs of the shuffled join (N > 1): slab k is probed while slab k+1 crosses NVLink")
     return ap.parse_args()
 
 
@@ -269,16 +273,14 @@ def run_ours(args):
     cap = npr if world == 1 else int(npr * 1.02) + 1_000_000
     out_cols = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in out_types]
     if world > 1:
+        from galaxysql_b200 import pipelines
         uid = torch.zeros(128, dtype=torch.uint8, device=dev)
         if rank == 0:
             uid.copy_(torch.tensor(list(api.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         api.comm_init(ctx, world, rank, bytes(uid.cpu().tolist()))
-        xb = api.Exchange(ctx, types, [0], world)
-        xp = api.Exchange(ctx, types, [0], world)
         bcap = int(nb * 1.05) + 1_000_000
-        rb = [(torch.empty(bcap, dtype=tt[t], device=dev), None) for t in types]
-        rp = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in types]
+        sj = pipelines.ShuffledJoin(ctx, N.JOIN_INNER, types, types, [0], [0], build_capacity=bcap, probe_capacity=cap, nslabs=args.slabs)
 
     def b(cols):
         return [(c, None) for c in cols]
@@ -287,26 +289,19 @@ def run_ours(args):
 
     def step_single():
         j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nb)
-        j.build_consume(b(build))
+        j.build_consume_ref(b(build))   # device-resident build side: referenced, not copied (gsql_join_build_consume_ref)
         j.build_finish()
         state["out_rows"] = j.probe_into(b(probe), out_cols, cap)
         state["info"] = j.info()
         j.close()
 
     def step_multi():
-        # exchange both sides on the join key, then join locally.  Measured dead ends (r01, N = 2): a slabbed variant that
-        # overlapped the AllToAllv of slab i+1 with the probe of slab i through a second context + host thread (125 ms vs
-        # 103 ms per step); running the join on a second context so that the table build overlaps the probe-side
-        # AllToAllv (228 ms vs 79 ms: the second context's memory pool re-grows every step); scattering the rank's own
-        # rows straight into the receive buffer instead of a self send/recv (scatter 9.8 -> 12.5 ms, AllToAllv unchanged).
-        nbr, _ = xb.all_to_all_into(b(build), rb, bcap)
-        npr_r, _ = xp.all_to_all_into(b(probe), rp, cap)
-        j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nbr)
-        j.build_consume([(c[:nbr], None) for c, _ in rb])
-        j.build_finish()
-        state["out_rows"] = j.probe_into([(c[:npr_r], None) for c, _ in rp], out_cols, cap)
-        state["info"] = j.info()
-        j.close()
+        # both sides are split by ExecUtils.partition(key) and written straight into the owning GPU's receive buffer over
+        # NVLink (gsql_xchg_push: no staging copy, no NCCL kernel); the build side's table is built from the receive
+        # buffer in place, and probe slab k is joined while slab k+1 is still on the wire (pipelines.ShuffledJoin).
+        sj.run(b(probe), b(build), out_cols=out_cols, out_capacity=cap)
+        state["out_rows"] = sj.last_rows
+        state["info"] = sj.last_info
 
     step = step_multi if world > 1 else step_single
 
@@ -354,10 +349,13 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = npr * world / (ms_step / 1000.0)
 
-    # ---- spot-check the last step's output on the device (parity proper lives in tests/)
+    # ---- parity of the last step's output, outside the timed region: an order-independent 64-bit checksum over EVERY
+    # output row (probe.key, p1, p2, build.key, b1, b2), all-reduced over the ranks, against the same checksum computed
+    # from the inputs (each probe row joined with its build row through the inverse of the build-key permutation).
+    # Equal sums <=> the distributed output is the global join's row multiset (up to a 2^-64 collision).
     n_out = state["out_rows"]
-    chk = min(n_out, 1 << 22)
-    assert bool((out_cols[0][0][:chk] == out_cols[3][0][:chk]).all()), "probe.key != build.key in the output"
+    parity = verify_join_checksum(torch, dist, synth, dev, world, rank, nb, npr, probe, out_cols, n_out)
+    assert parity["match"], f"join output checksum mismatch: {parity}"
 
     # ---- roofline of the dominant kernel(s): the probe phase
     probe_kernels = [k for k in prof if "probe" in k or k == "join_scan"]
@@ -365,10 +363,17 @@ def run_ours(args):
     probe_rows_rank = n_out
     peak, peak_src = measured_peak_gbs()
     achieved = PROBE_ALG_BYTES * probe_rows_rank / (probe_ms / 1000.0) / 1e9 if probe_ms > 0 else 0.0
-    # dram__bytes_read.sum + dram__bytes_write.sum of the probe-phase launches over 1 B probe rows, from the `ncu --set full`
-    # captures summarised in profiles/r01_ncu_summary.md.  Radix mode (prof_r01i/k): k_fj_hist 8.0 + k_fj_scatter 32.5 +
-    # k_fj_probe 51.1 GB.  One partition (prof_r01h): 173.95 GB — every random 16-byte table read costs a ~128-byte HBM fetch.
-    traffic = (173.95e9 if state["info"].partitions == 1 else 91.6e9) * (probe_rows_rank / 1e9)
+    # dram__bytes_read.sum + dram__bytes_write.sum per 1 B probe rows of the probe-phase kernels, from this round's committed
+    # `ncu --set full` capture (profiles/r02_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); null when the
+    # capture is absent or was taken for another table mode — never a number typed into this file
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        ent = tj.get("radix" if state["info"].partitions > 1 else "one_partition")
+        if ent:
+            traffic = float(ent["dram_bytes_per_probe_row"]) * probe_rows_rank
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "+".join(sorted(probe_kernels)), "kernel_ms_per_step": probe_ms,
                 "algorithmic_bytes_per_probe_row": PROBE_ALG_BYTES, "peak_source": peak_src,
@@ -420,6 +425,50 @@ def run_ours(args):
     if world > 1:
         ctx.lib.gsql_comm_destroy(ctx.ptr)
         dist.destroy_process_group()
+
+
+def _mix_rows(torch, key, p1, p2, b1, b2):
+    """64-bit mix of one joined row (int64 wraparound arithmetic); summed over rows it is order-independent."""
+    from galaxysql_b200 import synth
+    h = key * (-7046029254386353131) + p1.to(torch.int64) * (-4658895280553007687) + p2.to(torch.int64) * (-7723592293110705685)
+    h = synth.splitmix64_t(h) + b1.to(torch.int64) * 0x2545F4914F6CDD1D + b2.to(torch.int64) * 0x27D4EB2F165667C5
+    return synth.splitmix64_t(h)
+
+
+def verify_join_checksum(torch, dist, synth, dev, world, rank, nb, npr, probe, out_cols, n_out, chunk=1 << 26):
+    """Expected: every probe row (key, p1, p2) of this rank joined with THE build row of its key.  Build keys of rank r are
+    perm_r * world + r (perm_r = randperm(nb) seeded 42 + r, or seed 42 for world == 1), build payloads are counter-based
+    functions of the build row index — so any rank can reconstruct any build row from its key alone."""
+    inv = torch.empty(world * nb, dtype=torch.int32, device=dev)
+    for r in range(world):
+        g = torch.Generator(device=dev)
+        g.manual_seed(42 + r if world > 1 else 42)
+        perm = torch.randperm(nb, generator=g, device=dev, dtype=torch.int64)
+        inv[r * nb:(r + 1) * nb][perm] = torch.arange(nb, dtype=torch.int32, device=dev)
+        del perm
+    exp = torch.zeros((), dtype=torch.int64, device=dev)
+    for lo in range(0, npr, chunk):
+        hi = min(npr, lo + chunk)
+        k = probe[0][lo:hi]
+        i = inv[(k % world) * nb + k // world].to(torch.int64)
+        b1 = synth._top31(synth.splitmix64_t(i + (synth.SEED + 1 * synth._STREAM)))
+        b2 = synth._top31(synth.splitmix64_t(i + (synth.SEED + 2 * synth._STREAM)))
+        exp += _mix_rows(torch, k, probe[1][lo:hi], probe[2][lo:hi], b1, b2).sum()
+        del k, i, b1, b2
+    del inv
+    got = torch.zeros((), dtype=torch.int64, device=dev)
+    keys_equal = True
+    for lo in range(0, n_out, chunk):
+        hi = min(n_out, lo + chunk)
+        o = [c[0][lo:hi] for c in out_cols]
+        keys_equal = keys_equal and bool((o[0] == o[3]).all())
+        got += _mix_rows(torch, o[0], o[1], o[2], o[4], o[5]).sum()
+    t = torch.stack([exp, got, torch.tensor(n_out, dtype=torch.int64, device=dev)])
+    if world > 1:
+        dist.all_reduce(t)
+    e, g_, n = (int(v) for v in t.tolist())
+    return {"match": bool(e == g_ and n == npr * world and keys_equal), "expected": e, "got": g_, "rows": n,
+            "what": "sum over all output rows of mix64(probe.key,p1,p2,b1,b2), all ranks, vs the same sum derived from the inputs"}
 
 
 def run_aux_agg(ctx, api, N, synth, dev, scale, peak_gbs):

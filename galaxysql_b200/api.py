@@ -101,6 +101,7 @@ class Context:
                                   "galaxysql_b200 has no CPU fallback")
         self.ptr = p
         self.device = device
+        self.nranks, self.rank = 1, 0   # set by comm_init
 
     def close(self):
         if getattr(self, "ptr", None):
@@ -282,6 +283,13 @@ class HashJoin:
     def build_consume(self, cols):
         bv = _BatchView(cols)
         self.ctx.check(self.ctx.lib.gsql_join_build_consume(self.h, bv.ref()))
+
+    def build_consume_ref(self, cols):
+        """Zero-copy build side (one device-resident batch, e.g. the view an Exchange.recv returned): the columns are
+        referenced until close()."""
+        bv = _BatchView(cols)
+        self._build_ref = bv  # keeps the tensors alive as long as the handle references them
+        self.ctx.check(self.ctx.lib.gsql_join_build_consume_ref(self.h, bv.ref()))
 
     def build_finish(self):
         self.ctx.check(self.ctx.lib.gsql_join_build_finish(self.h))
@@ -481,6 +489,85 @@ class Exchange:
         return n.value, np.array(list(recv), dtype=np.int64)
 
 
+class _DevView:
+    """A typed window onto device memory the library owns (__cuda_array_interface__), so that torch can wrap it without a copy."""
+
+    def __init__(self, ptr: int, n: int, typestr: str, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {N.T_INT32: "<i4", N.T_INT64: "<i8", N.T_FP64: "<f8"}
+
+
+def _view_tensor(ctx: Context, ptr: int, n: int, t: Optional[int], owner):
+    dev = f"cuda:{ctx.device}"
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8 if t is None else _t_torch()[t], device=dev)
+    return torch.as_tensor(_DevView(ptr, n, "|u1" if t is None else _TYPESTR[t], owner), device=dev)
+
+
+def _exchange_open_p2p(self, capacity_rows: int, nullable: Sequence[int] = ()):
+    """Collective: allocate this rank's receive buffer (capacity_rows rows; the same value on every rank) and map every
+    peer's buffer (gsql_xchg_open_p2p)."""
+    mask = 0
+    for c in nullable:
+        mask |= 1 << c
+    self.ctx.check(self.ctx.lib.gsql_xchg_open_p2p(self.h, capacity_rows, mask))
+    self._nullable = set(nullable)
+
+
+def _exchange_push(self, cols, nslabs: int = 1):
+    """Collective, asynchronous: split `cols` (device) by destination rank and write every destination's rows straight
+    into its receive buffer over NVLink, slab after slab.  Returns the rows this rank receives per slab."""
+    bv = _BatchView(cols)
+    assert bv.mem == N.MEM_DEVICE
+    self._push_src = bv  # the input must stay alive until the slabs have been received
+    rows = (C.c_int64 * nslabs)()
+    total = C.c_int64()
+    st = self.ctx.lib.gsql_xchg_push(self.h, bv.ref(), nslabs, rows, C.byref(total))
+    self.ctx.check(st, total.value)
+    return [rows[i] for i in range(nslabs)]
+
+
+def _exchange_recv(self, slab: int = -1):
+    """The rows of slab `slab` of the last push (-1: all slabs as one batch) as zero-copy tensors over the receive
+    buffer; the context stream is made to wait for their arrival.  Valid until the next push."""
+    n = len(self.types)
+    carr = (N.Col * n)()
+    view = N.Batch(0, n, N.MEM_DEVICE, carr)
+    self.ctx.check(self.ctx.lib.gsql_xchg_recv_view(self.h, slab, C.byref(view)))
+    out = []
+    for c in range(n):
+        d = _view_tensor(self.ctx, carr[c].data or 0, view.rows, self.types[c], self)
+        nl = _view_tensor(self.ctx, carr[c].nulls or 0, view.rows, None, self) if carr[c].nulls else None
+        out.append((d, nl))
+    return out
+
+
+def _exchange_push_wait(self):
+    self.ctx.check(self.ctx.lib.gsql_xchg_push_wait(self.h))
+
+
+Exchange.open_p2p = _exchange_open_p2p
+Exchange.push = _exchange_push
+Exchange.recv = _exchange_recv
+Exchange.push_wait = _exchange_push_wait
+
+
+def plan_layout(nranks: int, nslabs: int, me: int, matrix):
+    """gsql_xchg_plan_layout (pure host arithmetic): matrix[src][slab][dst] -> (send_base[slab][dst], recv_base[slab][src],
+    slab_rows[slab], worst rank's total)."""
+    m = np.ascontiguousarray(matrix, dtype=np.int64).reshape(nranks, nslabs, nranks)
+    send = np.zeros((nslabs, nranks), dtype=np.int64)
+    recv = np.zeros((nslabs, nranks), dtype=np.int64)
+    rows = np.zeros(nslabs, dtype=np.int64)
+    p64 = C.POINTER(C.c_int64)
+    worst = N.load().gsql_xchg_plan_layout(nranks, nslabs, me, m.ctypes.data_as(p64), send.ctypes.data_as(p64),
+                                           recv.ctypes.data_as(p64), rows.ctypes.data_as(p64))
+    return send, recv, rows, int(worst)
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     st = N.load().gsql_comm_unique_id(buf)
@@ -492,3 +579,4 @@ def comm_unique_id() -> bytes:
 def comm_init(ctx: Context, nranks: int, rank: int, uid: bytes):
     buf = (C.c_uint8 * 128)(*uid)
     ctx.check(ctx.lib.gsql_comm_init(ctx.ptr, nranks, rank, buf))
+    ctx.nranks, ctx.rank = nranks, rank

@@ -26,7 +26,7 @@ namespace {
 
 constexpr unsigned long long DIGEST_EMPTY = 0x8000000000000000ULL;
 constexpr int GID_PENDING = -1;
-enum { C_NGROUPS = 0, C_OVERFLOW = 1, C_COUNT = 4 };
+enum { C_NGROUPS = 0, C_OVERFLOW = 1, /* 2 = C_FALLBACK (agg_fast.cuh) */ C_FATAL = 3, C_COUNT = 4 };
 
 struct __align__(16) ASlot {
     unsigned long long digest;
@@ -57,6 +57,7 @@ struct AggParams {
     const int64_t *row_list;       // non-null: process these rows (overflow re-run) instead of [row0, row0+rows)
     int64_t row0, rows;
     int64_t gcap;                  // groups the arrays can hold before a grow (a slack margin sits above it)
+    int64_t garr;                  // hard capacity of the by-gid arrays (gcap + slack): a gid beyond it is never stored
     int32_t n_derived, rf_col, rf_op, pad2;
     int32_t keycol[GSQL_MAX_KEYS];  // input column index of each group key
     int64_t rf_value;
@@ -141,9 +142,14 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
         }
         if (mine) {  // first appearance: allocate the dense group id, publish keys, then the id
             int gid = (int)atomicAdd(&P.counters[C_NGROUPS], 1ULL);
-            for (int c = 0; c < P.nkeys; c++) {
-                P.gkey[c][gid] = kv[c];
-                P.gnull[c][gid] = kn[c] ? 1 : 0;
+            if ((int64_t)gid >= P.garr) {  // cannot happen while the host grows after every launch (slack covers one launch's merges):
+                P.counters[C_FATAL] = 1;   // never write out of bounds — the host turns this into an error
+                gid = (int)(P.garr - 1);
+            } else {
+                for (int c = 0; c < P.nkeys; c++) {
+                    P.gkey[c][gid] = kv[c];
+                    P.gnull[c][gid] = kn[c] ? 1 : 0;
+                }
             }
             __threadfence();
             *reinterpret_cast<volatile int *>(&sl->gid) = gid;
@@ -586,6 +592,7 @@ static void agg_fill_params(gsql_agg *a, const StagedBatch *sb, AggParams *P) {
     P->counters = a->counters.as<unsigned long long>();
     P->overflow_rows = a->overflow.as<int64_t>();
     P->gcap = a->gcap;
+    P->garr = a->garr;
     for (int k = 0; k < a->nkeys; k++) P->keycol[k] = a->spec.groups[k];
     P->n_derived = a->spec.n_derived;
     for (int i = 0; i < a->spec.n_derived; i++) P->derived[i] = a->spec.derived[i];
@@ -743,6 +750,16 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     GSQL_TRY(validate_batch(ctx, batch, a->spec.n_input_cols, a->spec.input_types));
     if (batch->rows == 0) return GSQL_OK;
     GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    gsql_batch stripped;
+    gsql_col stripped_cols[GSQL_MAX_COLS];
+    {  // all-zero null masks are dropped: the privatised kernels keep their no-NULL shortcuts for a caller that always passes isNull[]
+        bool has_mask = false;
+        for (int i = 0; i < batch->ncols; i++) has_mask |= batch->cols[i].nulls != nullptr;
+        if (has_mask) {
+            GSQL_TRY(strip_zero_masks(ctx, batch, &stripped, stripped_cols));
+            batch = &stripped;
+        }
+    }
     StagedBatch sb;
     GSQL_TRY(stage_batch(ctx, batch, &sb));
     GSQL_TRY(a->overflow.grow(ctx, (size_t)batch->rows * 8, 0));
@@ -782,18 +799,11 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count, steps);
             if (grid < 1) grid = 1;
             if (LP.f64_shape) {  // opt-in specialisation (GSQL_AGG_LANE_F64=1)
-                static int attr_smem_f64 = 0;
-                if (LP.total > attr_smem_f64) {
-                    GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
-                    attr_smem_f64 = LP.total;
-                }
+                // per device, cheap: set before every launch (a process may drive several GPUs through several contexts)
+                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane_f64, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
                 k_agg_lane_f64<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
             } else {
-                static int attr_smem = 0;
-                if (LP.total > attr_smem) {
-                    GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
-                    attr_smem = LP.total;
-                }
+                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_lane, cudaFuncAttributeMaxDynamicSharedMemorySize, LP.total));
                 k_agg_lane<<<grid, LA_THREADS, LP.total, ctx->stream>>>(P, LP);
             }
         } else if (use_smem) {
@@ -801,11 +811,7 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
             int64_t warps = div_up(P.rows, 32);
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, div_up(warps, AF_THREADS / 32));
             if (grid < 1) grid = 1;
-            static int attr_smem = 0;
-            if (a->fast.L.total > attr_smem) {
-                GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, a->fast.L.total));
-                attr_smem = a->fast.L.total;
-            }
+            GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, a->fast.L.total));
             k_agg_smem<<<grid, AF_THREADS, a->fast.L.total, ctx->stream>>>(P, a->fast.L);
         } else {
             KernelScope ks(ctx, "agg_consume");
@@ -829,8 +835,27 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         }
         first = false;
         a->ngroups = (int64_t)h[C_NGROUPS];
+        if (h[C_FATAL]) {
+            ctx->sticky = true;
+            return gsql_set_error(ctx, GSQL_E_CAPACITY, "group arrays overflowed (%lld groups, capacity %lld)", (long long)a->ngroups, (long long)a->garr);
+        }
+        // the privatised kernels merge warp-private groups past gcap (into the slack): beyond a few tens of thousands of
+        // groups they cannot win any more, and every launch may add warps x S groups unchecked
+        if (a->ngroups > (1 << 16)) a->lane.enabled = a->fast.enabled = false;
         int64_t nover = (int64_t)h[C_OVERFLOW];
-        if (nover == 0) break;
+        if (nover == 0) {
+            // merges that ignored the cap may have eaten into the slack: restore it before the next launch
+            if (a->ngroups > a->gcap) {
+                int64_t ncap = a->gcap * 2;
+                while (ncap < a->ngroups) ncap *= 2;
+                GSQL_TRY(agg_resize(a, ncap, a->ngroups));
+                agg_fill_params(a, &sb, &P);
+                KernelScope ks(ctx, "agg_rehash");
+                k_agg_rehash<<<grid_rows(ctx, a->ngroups, 256, 8), 256, 0, ctx->stream>>>(P, a->ngroups);
+                GSQL_CUDA(ctx, cudaGetLastError());
+            }
+            break;
+        }
         // table full: double (at least) the group capacity, re-insert the groups, re-run only the overflowed rows
         GSQL_TRY(pending.alloc(ctx, (size_t)nover * 8));
         GSQL_CUDA(ctx, cudaMemcpyAsync(pending.p, a->overflow.p, (size_t)nover * 8, cudaMemcpyDeviceToDevice, ctx->stream));

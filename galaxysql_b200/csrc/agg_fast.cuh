@@ -400,8 +400,6 @@ struct AggFast {
 // Decides eligibility and the shared-memory layout (host).
 static void agg_fast_plan(AggFast *F, const gsql_agg_spec &spec, int nkeys, int naggs, const gsql_agg_call *aggs, const int32_t *in_type) {
     F->eligible = false;
-    for (int k = 0; k < nkeys; k++)
-        if (spec.input_types[spec.groups[k]] == GSQL_T_FP64 && false) return;
     for (int a = 0; a < naggs; a++)
         if (aggs[a].kind == GSQL_AGG_SUM && in_type[a] != GSQL_T_FP64) return;  // exact 128-bit SUM(int) stays generic
     int per_slot = 4 + nkeys * 9;

@@ -157,6 +157,12 @@ struct StagedBatch {
 };
 gsql_status stage_batch(gsql_ctx *ctx, const gsql_batch *in, StagedBatch *out);
 gsql_status validate_batch(gsql_ctx *ctx, const gsql_batch *b, int32_t expect_cols, const int32_t *expect_types);
+// any[i] = mask i holds a non-zero byte (masks[i] == nullptr -> false).  One kernel + one 4*n-byte read-back for device
+// masks, a word-wise host scan for host masks.  A Block that carries an all-zero boolean[] isNull (the reference allows
+// it: AbstractBlock.mayHaveNull() is only a hint) must not cost the NULL-free fast paths.
+gsql_status masks_any_null(gsql_ctx *ctx, int n, const uint8_t *const *masks, int64_t rows, int mem, bool *any);
+// Copy of `in` whose all-zero null masks are dropped (cols_storage: GSQL_MAX_COLS entries owned by the caller).
+gsql_status strip_zero_masks(gsql_ctx *ctx, const gsql_batch *in, gsql_batch *out, gsql_col *cols_storage);
 
 // ------------------------------------------------------------------------------------------------ hashing
 // fastutil HashCommon.mix (call sites ConcurrentRawHashTable.java:93,114; GroupOpenHashMap.java:143)

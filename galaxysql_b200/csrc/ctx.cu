@@ -289,6 +289,91 @@ gsql_status stage_batch(gsql_ctx *ctx, const gsql_batch *in, StagedBatch *out) {
     return GSQL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ null masks
+struct MaskSet {
+    const uint8_t *m[GSQL_MAX_COLS];
+    int32_t n;
+};
+__global__ void __launch_bounds__(256) k_any_null(const __grid_constant__ MaskSet M, int64_t rows, int32_t *__restrict__ any) {
+    for (int c = 0; c < M.n; c++) {
+        const uint8_t *m = M.m[c];
+        if (!m) continue;
+        // head bytes up to 16-byte alignment, 16-byte body, tail
+        const int64_t head = ((16 - ((uintptr_t)m & 15)) & 15) < rows ? (int64_t)((16 - ((uintptr_t)m & 15)) & 15) : rows;
+        const int64_t body = (rows - head) / 16;
+        const int4 *b = reinterpret_cast<const int4 *>(m + head);
+        int acc = 0;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < body; i += (int64_t)gridDim.x * blockDim.x) {
+            int4 v = __ldg(b + i);
+            acc |= v.x | v.y | v.z | v.w;
+        }
+        if (blockIdx.x == 0) {
+            for (int64_t i = threadIdx.x; i < head; i += blockDim.x) acc |= m[i];
+            for (int64_t i = head + body * 16 + threadIdx.x; i < rows; i += blockDim.x) acc |= m[i];
+        }
+        if (__any_sync(0xffffffffu, acc != 0) && (threadIdx.x & 31) == 0) any[c] = 1;
+    }
+}
+
+gsql_status masks_any_null(gsql_ctx *ctx, int n, const uint8_t *const *masks, int64_t rows, int mem, bool *any) {
+    bool some = false;
+    for (int i = 0; i < n; i++) { any[i] = false; some |= masks[i] != nullptr; }
+    if (!some || rows == 0) return GSQL_OK;
+    if (mem == GSQL_MEM_HOST) {
+        for (int i = 0; i < n; i++) {
+            const uint8_t *m = masks[i];
+            if (!m) continue;
+            int64_t r = 0;
+            for (; r < rows && ((uintptr_t)(m + r) & 7); r++) if (m[r]) { any[i] = true; break; }
+            if (any[i]) continue;
+            const uint64_t *w = reinterpret_cast<const uint64_t *>(m + r);
+            const int64_t nw = (rows - r) / 8;
+            uint64_t acc = 0;
+            for (int64_t k = 0; k < nw && !acc; k += 512) {
+                const int64_t e = k + 512 < nw ? k + 512 : nw;
+                for (int64_t q = k; q < e; q++) acc |= w[q];
+            }
+            if (acc) { any[i] = true; continue; }
+            for (r += nw * 8; r < rows; r++) if (m[r]) { any[i] = true; break; }
+        }
+        return GSQL_OK;
+    }
+    MaskSet M;
+    memset(&M, 0, sizeof(M));
+    M.n = n;
+    for (int i = 0; i < n; i++) M.m[i] = masks[i];
+    DevBuf flags;
+    GSQL_TRY(flags.alloc(ctx, (size_t)GSQL_MAX_COLS * 4));
+    GSQL_CUDA(ctx, cudaMemsetAsync(flags.p, 0, (size_t)GSQL_MAX_COLS * 4, ctx->stream));
+    {
+        KernelScope ks(ctx, "any_null");
+        int64_t g = div_up(rows / 16 + 1, 256);
+        if (g > (int64_t)ctx->sm_count * 8) g = (int64_t)ctx->sm_count * 8;
+        k_any_null<<<(int)g, 256, 0, ctx->stream>>>(M, rows, flags.as<int32_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    int32_t h[GSQL_MAX_COLS];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(h, flags.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) any[i] = h[i] != 0;
+    return GSQL_OK;
+}
+
+gsql_status strip_zero_masks(gsql_ctx *ctx, const gsql_batch *in, gsql_batch *out, gsql_col *cols_storage) {
+    *out = *in;
+    out->cols = cols_storage;
+    const uint8_t *masks[GSQL_MAX_COLS];
+    bool any[GSQL_MAX_COLS];
+    for (int i = 0; i < in->ncols; i++) {
+        cols_storage[i] = in->cols[i];
+        masks[i] = in->cols[i].nulls;
+    }
+    GSQL_TRY(masks_any_null(ctx, in->ncols, masks, in->rows, in->mem, any));
+    for (int i = 0; i < in->ncols; i++)
+        if (!any[i]) cols_storage[i].nulls = nullptr;
+    return GSQL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ hashing
 __global__ void __launch_bounds__(256) k_hash_rows(KeySet ks, int64_t rows, int32_t *__restrict__ out) {
     for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x)

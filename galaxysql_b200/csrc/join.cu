@@ -313,6 +313,9 @@ struct gsql_join {
     int32_t bkey_cols[GSQL_MAX_KEYS], pkey_cols[GSQL_MAX_KEYS];
     DevBuf bdata[GSQL_MAX_COLS], bnulls[GSQL_MAX_COLS];
     bool bhas_nulls[GSQL_MAX_COLS];
+    bool aliased = false;  // gsql_join_build_consume_ref: the build columns belong to the caller
+    const void *alias_data[GSQL_MAX_COLS];
+    const uint8_t *alias_nulls[GSQL_MAX_COLS];
     int64_t build_rows = 0, build_cap = 0;
     // table
     DevBuf slots, links, used, flags;
@@ -452,6 +455,7 @@ extern "C" gsql_status gsql_join_build_consume(gsql_join *j, const gsql_batch *b
     gsql_ctx *ctx = j->ctx;
     if (ctx->sticky) return GSQL_E_CUDA;
     if (j->built) return gsql_set_error(ctx, GSQL_E_STATE, "build_consume after build_finish");
+    if (j->aliased) return gsql_set_error(ctx, GSQL_E_STATE, "build_consume after build_consume_ref");
     GSQL_TRY(validate_batch(ctx, b, j->n_build, j->build_types));
     if (b->rows == 0) return GSQL_OK;
     if (j->build_rows + b->rows > 0x7fffffffLL) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "build side exceeds 2^31-1 rows");
@@ -477,11 +481,36 @@ extern "C" gsql_status gsql_join_build_consume(gsql_join *j, const gsql_batch *b
     return GSQL_OK;
 }
 
+extern "C" gsql_status gsql_join_build_consume_ref(gsql_join *j, const gsql_batch *b) {
+    if (!j) return GSQL_E_INVALID;
+    gsql_ctx *ctx = j->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (j->built) return gsql_set_error(ctx, GSQL_E_STATE, "build_consume_ref after build_finish");
+    GSQL_TRY(validate_batch(ctx, b, j->n_build, j->build_types));
+    if (b->mem != GSQL_MEM_DEVICE) return gsql_join_build_consume(j, b);  // host batches have to be uploaded anyway
+    if (j->aliased || j->build_rows != 0) return gsql_set_error(ctx, GSQL_E_STATE, "build_consume_ref takes the whole build side as one batch");
+    if (b->rows > 0x7fffffffLL) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "build side exceeds 2^31-1 rows");
+    if (b->rows == 0) return GSQL_OK;
+    j->aliased = true;
+    for (int i = 0; i < j->n_build; i++) {
+        j->alias_data[i] = b->cols[i].data;
+        j->alias_nulls[i] = b->cols[i].nulls;
+        j->bhas_nulls[i] = b->cols[i].nulls != nullptr;
+    }
+    j->build_rows = b->rows;
+    return GSQL_OK;
+}
+
+static const uint8_t *build_mask(const gsql_join *j, int i) {
+    if (!j->bhas_nulls[i]) return nullptr;
+    return j->aliased ? j->alias_nulls[i] : j->bnulls[i].as<uint8_t>();
+}
+
 static void fill_build_cols(gsql_join *j, DColSet *build, KeySet *bkeys) {
     build->n = j->n_build;
     for (int i = 0; i < j->n_build; i++) {
-        build->c[i].data = j->bdata[i].p;
-        build->c[i].nulls = j->bhas_nulls[i] ? j->bnulls[i].as<uint8_t>() : nullptr;
+        build->c[i].data = j->aliased ? j->alias_data[i] : j->bdata[i].p;
+        build->c[i].nulls = build_mask(j, i);
         build->c[i].type = j->build_types[i];
         build->c[i].pad = 0;
     }
@@ -561,18 +590,10 @@ static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::La
         KernelScope ks(ctx, name.c_str());
         FJ_DISPATCH_W(W, {
             if (pipe) {
-                static int attr_smem = 0;
-                if ((int)smem > attr_smem) {
                     GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_smem = (int)smem;
-                }
                 fj::k_fj_scatter<WW, true><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
             } else {
-                static int attr_smem = 0;
-                if ((int)smem > attr_smem) {
                     GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                    attr_smem = (int)smem;
-                }
                 fj::k_fj_scatter<WW, false><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
             }
         });
@@ -735,6 +756,14 @@ extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
     if (j->built) return GSQL_OK;
     GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
     const gsql_join_spec &s = j->spec;
+    {  // a mask that never flagged a row is no mask: it must not cost the NULL-free fast path (a JNI caller hands over every Block's isNull[])
+        const uint8_t *masks[GSQL_MAX_COLS];
+        bool any[GSQL_MAX_COLS];
+        for (int i = 0; i < j->n_build; i++) masks[i] = build_mask(j, i);
+        GSQL_TRY(masks_any_null(ctx, j->n_build, masks, j->build_rows, GSQL_MEM_DEVICE, any));
+        for (int i = 0; i < j->n_build; i++)
+            if (j->bhas_nulls[i] && !any[i]) { j->bhas_nulls[i] = false; j->bnulls[i].release(); }
+    }
     // pass-through / pass-nothing (ParallelHashJoinExec.buildConsume:107-128; doSpecialCheckForSemiJoin:290-310)
     if (j->build_rows == 0 && s.join_type == GSQL_JOIN_INNER) j->pass_nothing = true;
     if (j->semi_join) {
@@ -744,7 +773,7 @@ extern "C" gsql_status gsql_join_build_finish(gsql_join *j) {
         } else if (s.join_type == GSQL_JOIN_ANTI && s.n_anti_operands > 0 && j->n_build == 1 && j->bhas_nulls[0]) {
             // x NOT IN (... NULL ...) is never true: need to know whether the single build column holds a NULL
             std::vector<uint8_t> h((size_t)j->build_rows);
-            GSQL_CUDA(ctx, cudaMemcpyAsync(h.data(), j->bnulls[0].p, (size_t)j->build_rows, cudaMemcpyDeviceToHost, ctx->stream));
+            GSQL_CUDA(ctx, cudaMemcpyAsync(h.data(), build_mask(j, 0), (size_t)j->build_rows, cudaMemcpyDeviceToHost, ctx->stream));
             GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             for (uint8_t v : h)
                 if (v) { j->pass_nothing = true; break; }
@@ -967,11 +996,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         int grid = (int)(ntiles < (int64_t)ctx->sm_count * per_sm ? ntiles : (int64_t)ctx->sm_count * per_sm);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                              \
     if (PW == PWv && BW == BWv) {                                                                                                            \
-        static int attr_smem = 0;                                                                                                            \
-        if ((int)smem > attr_smem) {                                                                                                         \
             GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_tma<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-            attr_smem = (int)smem;                                                                                                           \
-        }                                                                                                                                    \
         fj::k_fj_probe_tma<PWv, BWv><<<grid, fj::PT_THREADS, smem, ctx->stream>>>(src, m, F.table.as<unsigned long long>(), F.nslots, O, cursor, \
                                                                                ticket, F.flags.as<int32_t>());                               \
     }
@@ -989,11 +1014,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         int grid = (int)(ntiles < (int64_t)ctx->sm_count * 2 ? ntiles : (int64_t)ctx->sm_count * 2);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                             \
     if (PW == PWv && BW == BWv) {                                                                                                           \
-        static int attr_smem = 0;                                                                                                           \
-        if ((int)smem > attr_smem) {                                                                                                        \
             GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe_pipe<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-            attr_smem = (int)smem;                                                                                                          \
-        }                                                                                                                                   \
         int per_sm = 0;                                                                                                                     \
         GSQL_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fj::k_fj_probe_pipe<PWv, BWv>, fj::THREADS, smem));           \
         if (per_sm < 1) per_sm = 1;                                                                                                         \
@@ -1014,11 +1035,7 @@ static gsql_status fast_probe_rows(gsql_join *j, const DColSet &cols, int64_t m,
         size_t smem = fj::stage_words_bytes(PW, BW, fj::TILE);
 #define FJ_PROBE_CASE(PWv, BWv)                                                                                                            \
     if (PW == PWv && BW == BWv) {                                                                                                          \
-        static int attr_smem = 0;                                                                                                          \
-        if ((int)smem > attr_smem) {                                                                                                       \
             GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_probe<PWv, BWv>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-            attr_smem = (int)smem;                                                                                                         \
-        }                                                                                                                                  \
         fj::k_fj_probe<PWv, BWv><<<grid, fj::THREADS, smem, ctx->stream>>>(src, cols, F.pl, m, F.table.as<unsigned long long>(), F.nslots, O, \
                                                                           cursor, F.flags.as<int32_t>());                                  \
     }
@@ -1250,6 +1267,16 @@ extern "C" gsql_status gsql_join_probe(gsql_join *j, const gsql_batch *probe, gs
         return GSQL_OK;
     }
     ProbeWork w;
+    gsql_batch stripped;
+    gsql_col stripped_cols[GSQL_MAX_COLS];
+    if (j->fast.enabled) {  // all-zero null masks are dropped before the path is chosen
+        bool has_mask = false;
+        for (int i = 0; i < probe->ncols; i++) has_mask |= probe->cols[i].nulls != nullptr;
+        if (has_mask) {
+            GSQL_TRY(strip_zero_masks(ctx, probe, &stripped, stripped_cols));
+            probe = &stripped;
+        }
+    }
     {
         gsql_status ferr = GSQL_OK;
         bool fast = fast_probe_applicable(j, probe, out, out_capacity, &ferr);

@@ -145,12 +145,30 @@ int grid_rows(gsql_ctx *ctx, int64_t rows, int block, int per_sm) {
 
 }  // namespace
 
+struct P2PCtrl;
+
 struct gsql_xchg {
     gsql_ctx *ctx;
     gsql_xchg_spec spec;
-    // send staging of the shuffle (partition-ordered columns), kept across calls: a shuffle of N rows stages N rows,
+    // send staging of the NCCL shuffle (partition-ordered columns), kept across calls: a shuffle of N rows stages N rows,
     // and re-allocating those gigabytes on every call raced the stream-ordered frees of the previous one
     DevBuf sdata[GSQL_MAX_COLS], snull[GSQL_MAX_COLS];
+    // ---- partition-and-push over peer memory (gsql_xchg_open_p2p)
+    bool p2p = false;
+    char *base = nullptr;                       // this rank's allocation: control block, then the receive columns
+    char *peer_base[GSQL_MAX_RANKS] = {nullptr};  // the same allocation of every rank, mapped here (CUDA IPC); [rank] = base
+    size_t alloc_bytes = 0;
+    int64_t cap = 0;
+    int64_t col_off[GSQL_MAX_COLS], null_off[GSQL_MAX_COLS];
+    cudaStream_t pstream = nullptr;             // pushes and their barriers run here, beside the context stream
+    cudaEvent_t in_ev = nullptr, slab_ev[GSQL_MAX_SLABS] = {nullptr};
+    unsigned long long seq = 0;                 // barrier sequence number (identical on all ranks: calls are collective)
+    int64_t pushes = 0;
+    int32_t last_slabs = 0;
+    int64_t slab_rows[GSQL_MAX_SLABS], slab_base[GSQL_MAX_SLABS];
+    DevBuf hist[GSQL_MAX_SLABS], offs[GSQL_MAX_SLABS], scan_tmp;
+    long long *host_matrix = nullptr;           // pinned: counts[src][slab][dst] of the current push
+    int32_t *host_err = nullptr;                // pinned copy of the control block's error word
 };
 
 extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spec, gsql_xchg **out) {
@@ -172,10 +190,13 @@ extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spe
     return GSQL_OK;
 }
 
+static void p2p_close(gsql_xchg *x);
+
 extern "C" void gsql_xchg_destroy(gsql_xchg *x) {
     if (!x) return;
     gsql_ctx *ctx = x->ctx;
     cudaSetDevice(ctx->device);
+    p2p_close(x);
     delete x;
     if (!ctx->sticky) cudaStreamSynchronize(ctx->stream);  // stream-ordered frees have really happened (see gsql_join_destroy)
     gsql_ctx_release(ctx);
@@ -335,12 +356,7 @@ extern "C" gsql_status gsql_comm_destroy(gsql_ctx *ctx) {
     return GSQL_OK;
 }
 
-// ---- opt-in slabbed shuffle (GSQL_XCHG_SLABS=S > 1; parity-checked on one B200 rank at the end of r01, performance not measured yet) -----------
-// The sequential path partitions the whole batch, then sends it: the scatter pass (HBM-bound) and the AllToAllv
-// (NVLink-bound) never overlap.  Here the batch is cut into S row slabs.  All S histograms run first (keys only), one
-// count exchange covers every (slab, destination) pair, and then slab i+1 is scattered on the context stream while the
-// segments of slab i travel on the stripe streams.  Receive layout is the sequential path's: per source rank contiguous
-// (its slabs one after the other).
+// XParams of the row range [row0, row0 + rows) of a staged batch (a slab of a push).
 static void fill_xparams(gsql_xchg *x, const StagedBatch &sb, int64_t row0, int64_t rows, XParams *Pp) {
     const gsql_xchg_spec &s = x->spec;
     XParams &P = *Pp;
@@ -367,133 +383,6 @@ static void fill_xparams(gsql_xchg *x, const StagedBatch &sb, int64_t row0, int6
     P.nblocks = nblocks;
 }
 
-static gsql_status all_to_all_slabbed(gsql_xchg *x, const StagedBatch &sb, gsql_batch *out, int64_t out_capacity, int64_t *out_rows,
-                                      int64_t *recv_counts, int S) {
-    gsql_ctx *ctx = x->ctx;
-    const gsql_xchg_spec &s = x->spec;
-    NcclApi *api = nccl_api();
-    const int R = ctx->nranks, K = ctx->n_extra;  // all NCCL traffic on the stripe streams: the context stream keeps scattering
-    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const int64_t n = sb.rows;
-    const int64_t SR = div_up(div_up(n > 0 ? n : 1, S), XBLOCK) * XBLOCK;  // rows per slab (the last ones may be short or empty)
-    DevBuf *sdata = x->sdata, *snull = x->snull;
-    for (int c = 0; c < s.n_cols; c++) {
-        GSQL_TRY(sdata[c].grow(ctx, (size_t)(n > 0 ? n : 1) * gsql_type_width(s.types[c]), 0));
-        if (out->cols[c].nulls) GSQL_TRY(snull[c].grow(ctx, (size_t)(n > 0 ? n : 1), 0));
-    }
-    // ---- 1. histograms + scans of every slab
-    std::vector<XParams> P((size_t)S);
-    std::vector<DevBuf> hist((size_t)S), offs((size_t)S);
-    std::vector<int64_t> rows_of((size_t)S, 0);
-    DevBuf tmp;
-    size_t tmp_bytes = 0;
-    for (int i = 0; i < S; i++) {
-        const int64_t lo = (int64_t)i * SR;
-        rows_of[(size_t)i] = lo < n ? (n - lo < SR ? n - lo : SR) : 0;
-        fill_xparams(x, sb, lo < n ? lo : 0, rows_of[(size_t)i], &P[(size_t)i]);
-        const int64_t nh = (int64_t)s.nparts * P[(size_t)i].nblocks;
-        GSQL_TRY(hist[(size_t)i].alloc(ctx, (size_t)(nh + 1) * 8));
-        GSQL_TRY(offs[(size_t)i].alloc(ctx, (size_t)(nh + 1) * 8));
-        GSQL_CUDA(ctx, cudaMemsetAsync(hist[(size_t)i].p, 0, (size_t)(nh + 1) * 8, ctx->stream));
-        size_t tb = 0;
-        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, hist[(size_t)i].as<int64_t>(), offs[(size_t)i].as<int64_t>(), nh + 1, ctx->stream));
-        if (tb > tmp_bytes) tmp_bytes = tb;
-    }
-    GSQL_TRY(tmp.alloc(ctx, tmp_bytes));
-    for (int i = 0; i < S; i++) {
-        const int64_t nh = (int64_t)s.nparts * P[(size_t)i].nblocks;
-        if (rows_of[(size_t)i] > 0) {
-            KernelScope ks(ctx, "xchg_hist");
-            k_xchg_hist<<<P[(size_t)i].nblocks, XBLOCK, s.nparts * sizeof(unsigned int), ctx->stream>>>(P[(size_t)i], hist[(size_t)i].as<int64_t>());
-        }
-        size_t tb = tmp_bytes;
-        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp.p, tb, hist[(size_t)i].as<int64_t>(), offs[(size_t)i].as<int64_t>(), nh + 1, ctx->stream));
-    }
-    GSQL_CUDA(ctx, cudaGetLastError());
-    // ---- 2. counts[slab][dst] to the host, one AllGather of S x R counts
-    std::vector<int64_t> starts((size_t)S * (R + 1), 0), counts((size_t)S * R, 0);
-    for (int i = 0; i < S; i++)
-        GSQL_CUDA(ctx, cudaMemcpy2DAsync(&starts[(size_t)i * (R + 1)], 8, offs[(size_t)i].p, (size_t)P[(size_t)i].nblocks * 8, 8, (size_t)R,
-                                         cudaMemcpyDeviceToHost, ctx->stream));
-    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (int i = 0; i < S; i++) {
-        starts[(size_t)i * (R + 1) + R] = rows_of[(size_t)i];
-        for (int d = 0; d < R; d++) counts[(size_t)i * R + d] = starts[(size_t)i * (R + 1) + d + 1] - starts[(size_t)i * (R + 1) + d];
-    }
-    DevBuf d_counts, d_matrix;
-    GSQL_TRY(d_counts.alloc(ctx, (size_t)S * R * 8));
-    GSQL_TRY(d_matrix.alloc(ctx, (size_t)R * S * R * 8));
-    GSQL_CUDA(ctx, cudaMemcpyAsync(d_counts.p, counts.data(), (size_t)S * R * 8, cudaMemcpyHostToDevice, ctx->stream));
-    GSQL_NCCL(ctx, api->AllGather(d_counts.p, d_matrix.p, (size_t)S * R, ncclInt64, comm, ctx->stream));
-    std::vector<int64_t> M((size_t)R * S * R);  // M[src][slab][dst]
-    GSQL_CUDA(ctx, cudaMemcpyAsync(M.data(), d_matrix.p, M.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int me = ctx->rank;
-    auto m_at = [&](int src, int slab, int dst) -> int64_t { return M[((size_t)src * S + slab) * R + dst]; };
-    std::vector<int64_t> rbase((size_t)R, 0);  // first receive row of each source
-    int64_t total = 0;
-    for (int src = 0; src < R; src++) {
-        rbase[(size_t)src] = total;
-        int64_t from = 0;
-        for (int i = 0; i < S; i++) from += m_at(src, i, me);
-        if (recv_counts) recv_counts[src] = from;
-        total += from;
-    }
-    *out_rows = total;
-    if (total > out_capacity) return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
-    // ---- 3. scatter slab i (context stream), then its segments leave on the stripe streams while slab i+1 is scattered
-    KernelScope ks(ctx, "xchg_alltoall");
-    std::vector<int64_t> rdone((size_t)R, 0);  // rows already received from each source (earlier slabs)
-    for (int i = 0; i < S; i++) {
-        const int64_t lo = (int64_t)i * SR;
-        if (rows_of[(size_t)i] > 0) {
-            XOut O;
-            memset(&O, 0, sizeof(O));
-            for (int c = 0; c < s.n_cols; c++) {
-                O.data[c] = (char *)sdata[c].p + (size_t)lo * gsql_type_width(s.types[c]);
-                if (out->cols[c].nulls) O.nulls[c] = snull[c].as<uint8_t>() + lo;
-            }
-            k_xchg_scatter<<<P[(size_t)i].nblocks, XBLOCK, s.nparts * sizeof(unsigned long long), ctx->stream>>>(P[(size_t)i], offs[(size_t)i].as<int64_t>(), O);
-            GSQL_CUDA(ctx, cudaGetLastError());
-        }
-        cudaEvent_t ready;
-        GSQL_CUDA(ctx, cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        GSQL_CUDA(ctx, cudaEventRecord(ready, ctx->stream));
-        for (int k = 0; k < K; k++) {
-            ncclComm_t cm = (ncclComm_t)ctx->nccl_extra[k];
-            cudaStream_t st = ctx->xstreams[k];
-            GSQL_CUDA(ctx, cudaStreamWaitEvent(st, ready, 0));
-            GSQL_NCCL(ctx, api->GroupStart());
-            for (int c = 0; c < s.n_cols; c++) {
-                const size_t w = (size_t)gsql_type_width(s.types[c]);
-                for (int peer = 0; peer < R; peer++) {
-                    const int64_t ns = counts[(size_t)i * R + peer], nr = m_at(peer, i, me);
-                    const int64_t soff = lo + starts[(size_t)i * (R + 1) + peer], roff = rbase[(size_t)peer] + rdone[(size_t)peer];
-                    const int64_t s0 = ns * k / K, s1 = ns * (k + 1) / K, r0 = nr * k / K, r1 = nr * (k + 1) / K;
-                    if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)sdata[c].p + (size_t)(soff + s0) * w, (size_t)(s1 - s0) * w, ncclInt8, peer, cm, st));
-                    if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].data + (size_t)(roff + r0) * w, (size_t)(r1 - r0) * w, ncclInt8, peer, cm, st));
-                    if (out->cols[c].nulls) {
-                        if (s1 > s0) GSQL_NCCL(ctx, api->Send((char *)snull[c].p + soff + s0, (size_t)(s1 - s0), ncclInt8, peer, cm, st));
-                        if (r1 > r0) GSQL_NCCL(ctx, api->Recv((char *)out->cols[c].nulls + roff + r0, (size_t)(r1 - r0), ncclInt8, peer, cm, st));
-                    }
-                }
-            }
-            GSQL_NCCL(ctx, api->GroupEnd());
-        }
-        GSQL_CUDA(ctx, cudaEventDestroy(ready));
-        for (int peer = 0; peer < R; peer++) rdone[(size_t)peer] += m_at(peer, i, me);
-    }
-    for (int k = 0; k < K; k++) {  // join the stripes back into the context stream
-        cudaEvent_t done;
-        GSQL_CUDA(ctx, cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-        GSQL_CUDA(ctx, cudaEventRecord(done, ctx->xstreams[k]));
-        GSQL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, done, 0));
-        GSQL_CUDA(ctx, cudaEventDestroy(done));
-    }
-    out->rows = total;
-    return GSQL_OK;
-}
-
 extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t out_capacity,
                                             int64_t *out_rows, int64_t *recv_counts) {
     if (!x || !in || !out || !out_rows) return GSQL_E_INVALID;
@@ -510,13 +399,11 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     const int R = ctx->nranks;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     // nullable columns must be nullable on every rank (collective shape): decided by the output buffers
+    for (int c = 0; c < s.n_cols; c++)
+        if (in->cols[c].nulls && !out->cols[c].nulls) return gsql_set_error(ctx, GSQL_E_INVALID, "output column %d needs a nulls buffer", c);
     // ---- 1. partition into contiguous per-destination segments
     StagedBatch sb;
     GSQL_TRY(stage_batch(ctx, in, &sb));
-    {
-        const int slabs = getenv("GSQL_XCHG_SLABS") ? atoi(getenv("GSQL_XCHG_SLABS")) : 1;  // every rank must use the same value
-        if (slabs > 1 && slabs <= 64 && ctx->n_extra > 0) return all_to_all_slabbed(x, sb, out, out_capacity, out_rows, recv_counts, slabs);
-    }
     XOut O;
     memset(&O, 0, sizeof(O));
     DevBuf *sdata = x->sdata, *snull = x->snull;
@@ -533,14 +420,25 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     DevBuf offs;
     if (in->rows > 0) GSQL_TRY(partition_device(x, sb, O, &offs, send_counts.data()));
     // ---- 2. exchange the R x R count matrix
+    // every rank also publishes its receive capacity: whether ANY rank overflows is then decided identically everywhere
+    // (a rank that returned E_CAPACITY on its own would leave the others blocked inside the grouped send/recv)
     DevBuf d_counts, d_matrix;
-    GSQL_TRY(d_counts.alloc(ctx, (size_t)R * 8));
-    GSQL_TRY(d_matrix.alloc(ctx, (size_t)R * R * 8));
-    GSQL_CUDA(ctx, cudaMemcpyAsync(d_counts.p, send_counts.data(), (size_t)R * 8, cudaMemcpyHostToDevice, ctx->stream));
-    GSQL_NCCL(ctx, api->AllGather(d_counts.p, d_matrix.p, (size_t)R, ncclInt64, comm, ctx->stream));
-    std::vector<int64_t> matrix((size_t)R * R);
-    GSQL_CUDA(ctx, cudaMemcpyAsync(matrix.data(), d_matrix.p, (size_t)R * R * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_TRY(d_counts.alloc(ctx, (size_t)(R + 1) * 8));
+    GSQL_TRY(d_matrix.alloc(ctx, (size_t)R * (R + 1) * 8));
+    send_counts.push_back(out_capacity);
+    GSQL_CUDA(ctx, cudaMemcpyAsync(d_counts.p, send_counts.data(), (size_t)(R + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GSQL_NCCL(ctx, api->AllGather(d_counts.p, d_matrix.p, (size_t)(R + 1), ncclInt64, comm, ctx->stream));
+    std::vector<int64_t> wide((size_t)R * (R + 1)), matrix((size_t)R * R);
+    GSQL_CUDA(ctx, cudaMemcpyAsync(wide.data(), d_matrix.p, wide.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int src = 0; src < R; src++)
+        for (int dst = 0; dst < R; dst++) matrix[(size_t)src * R + dst] = wide[(size_t)src * (R + 1) + dst];
+    bool someone_overflows = false;
+    for (int dst = 0; dst < R; dst++) {
+        int64_t need = 0;
+        for (int src = 0; src < R; src++) need += matrix[(size_t)src * R + dst];
+        if (need > wide[(size_t)dst * (R + 1) + R]) someone_overflows = true;
+    }
     int64_t total = 0;
     std::vector<int64_t> roff((size_t)R), soff((size_t)R);
     for (int src = 0; src < R; src++) {
@@ -555,10 +453,9 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
         acc += send_counts[(size_t)dst];
     }
     *out_rows = total;
-    // capacity must be judged identically by all ranks or the collective below would hang: every rank can see the
-    // whole matrix, so all of them learn whether anyone overflows... each rank has its own capacity, so the caller
-    // contract is: size `out` for the worst case (sum over sources) or retry collectively.
-    if (total > out_capacity) return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all needs %lld rows, capacity %lld", (long long)total, (long long)out_capacity);
+    if (someone_overflows)  // on every rank alike: nobody enters the exchange
+        return gsql_set_error(ctx, GSQL_E_CAPACITY, "all_to_all: a rank's receive buffer is too small (this rank needs %lld rows, capacity %lld)",
+                              (long long)total, (long long)out_capacity);
     // ---- 3. AllToAllv: grouped send/recv per column (and per null mask), striped over 1 + n_extra communicators /
     //         streams so that several NCCL p2p kernels run side by side
     {
@@ -598,5 +495,536 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
         GSQL_CUDA(ctx, cudaEventDestroy(ready));
     }
     out->rows = total;
+    return GSQL_OK;
+}
+
+
+// ================================================================================================ partition-and-push
+// One-pass shuffle over peer-mapped memory (gsql_xchg_open_p2p / _push / _recv_view).  Per rank ONE device allocation
+// holds a control block and the receive columns; CUDA IPC maps it into every peer.  A push:
+//   1. k_xchg_hist per slab (keys only) + exclusive scan  -> rows per (slab, destination, block)
+//   2. k_p2p_publish: every rank writes its counts[slab][dst] into every peer's control block, then all ranks meet in a
+//      flag barrier (st.release.sys / ld.acquire.sys on the peer-mapped flags) -> each rank reads the whole
+//      counts[src][slab][dst] matrix locally and derives, on the host, where every (src, slab) segment starts in every
+//      receive buffer (gsql_xchg_plan_layout): slab-major, source-minor, so a slab is one contiguous batch.
+//   3. per slab k_xchg_push: a block splits 2048-row tiles by destination in shared memory (warp match.any ranks, one
+//      block scan of the (destination, warp, row-slot) cells) and writes each destination's run of every column with
+//      coalesced stores straight into that GPU's receive buffer over NVLink (self = local HBM); then k_p2p_barrier.
+// No staging buffer, no NCCL kernel on the data path; the consumer of slab k (join probe, aggregation) runs on the
+// context stream while slab k+1 is being pushed on the exchange's stream.
+namespace {
+
+constexpr int PUSH_THREADS = 512;
+constexpr int PUSH_RPT = 4;
+constexpr int PUSH_TILE = PUSH_THREADS * PUSH_RPT;
+constexpr int PUSH_WARPS = PUSH_THREADS / 32;
+constexpr int PUSH_CELLS = PUSH_WARPS * PUSH_RPT;  // (warp, row-slot) cells per destination
+constexpr size_t CTRL_BYTES = 512 * 1024;
+
+}  // namespace
+
+struct P2PCtrl {                                   // first bytes of every rank's peer-mapped allocation
+    unsigned long long flag[GSQL_MAX_RANKS];       // flag[src]: last barrier sequence number rank src arrived at
+    int32_t err;                                   // local only: a barrier timed out
+    int32_t pad[31];
+    long long counts[2][GSQL_MAX_RANKS][GSQL_MAX_SLABS][GSQL_MAX_RANKS];  // [push parity][src][slab][dst], written by src
+};
+static_assert(sizeof(P2PCtrl) <= CTRL_BYTES, "control block must fit its region");
+
+namespace {
+
+struct PeerSet {
+    P2PCtrl *ctrl[GSQL_MAX_RANKS];
+    int32_t nranks, me;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All ranks meet: thread t tells rank t "I arrived at seq" and waits until rank t has told this rank the same.  Everything
+// this rank wrote to peer memory before (earlier kernels of the stream, or this kernel before the __syncthreads) is
+// visible to a peer that has passed its own barrier.  Bounded: a peer that never arrives sets err instead of hanging.
+__device__ __forceinline__ void p2p_barrier(const PeerSet &S, unsigned long long seq) {
+    __syncthreads();
+    if ((int)threadIdx.x < S.nranks) {
+        __threadfence_system();
+        st_release_sys(&S.ctrl[threadIdx.x]->flag[S.me], seq);
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(&S.ctrl[S.me]->flag[threadIdx.x]) < seq) {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > 30000000000ULL) {  // 30 s
+                S.ctrl[S.me]->err = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+struct SlabOffs {
+    const int64_t *offs[GSQL_MAX_SLABS];  // [dst][block] exclusive scan of slab i (+ one total entry)
+    int32_t nblocks[GSQL_MAX_SLABS];
+    int32_t nslabs, parity;
+};
+
+__global__ void __launch_bounds__(256) k_p2p_publish(const __grid_constant__ PeerSet S, const __grid_constant__ SlabOffs O, unsigned long long seq) {
+    const int R = S.nranks;
+    for (int i = threadIdx.x; i < O.nslabs * R; i += blockDim.x) {
+        const int slab = i / R, dst = i % R;
+        const int64_t *o = O.offs[slab];
+        const int nb = O.nblocks[slab];
+        const long long cnt = (long long)(o[(int64_t)(dst + 1) * nb] - o[(int64_t)dst * nb]);
+        for (int p = 0; p < R; p++) S.ctrl[p]->counts[O.parity][S.me][slab][dst] = cnt;
+    }
+    p2p_barrier(S, seq);
+}
+
+__global__ void __launch_bounds__(32) k_p2p_barrier(const __grid_constant__ PeerSet S, unsigned long long seq) { p2p_barrier(S, seq); }
+
+struct PushParams {
+    XParams X;                              // the slab: input columns, key channels, nparts = ranks, block geometry
+    const int64_t *offs;                    // [dst][block] exclusive scan of this slab
+    int64_t base_row[GSQL_MAX_RANKS];       // first row of this rank's (slab) segment in dst's receive buffer
+    char *peer_base[GSQL_MAX_RANKS];        // dst's allocation, mapped here
+    int64_t col_off[GSQL_MAX_COLS];         // byte offset of column c inside an allocation
+    int64_t null_off[GSQL_MAX_COLS];        // byte offset of column c's NULL bytes, or -1
+};
+
+__global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_constant__ PushParams P) {
+    __shared__ __align__(16) unsigned long long stage[2][PUSH_TILE];  // one column of the tile in destination order (double-buffered)
+    __shared__ unsigned char sdest[PUSH_TILE];                        // destination of each staged position
+    __shared__ unsigned int cell[GSQL_MAX_RANKS * PUSH_CELLS];        // rows per (dst, warp, slot) -> exclusive starts
+    __shared__ unsigned long long cur[GSQL_MAX_RANKS];                // next row of this block in dst's receive buffer
+    __shared__ unsigned int dstart[GSQL_MAX_RANKS + 1];
+    typedef cub::BlockScan<unsigned int, PUSH_THREADS> BlockScan;
+    __shared__ typename BlockScan::TempStorage scan_tmp;
+    const int R = P.X.nparts;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = P.X.nblocks;
+    if (tid < R) cur[tid] = (unsigned long long)(P.base_row[tid] + (P.offs[(int64_t)tid * nb + blockIdx.x] - P.offs[(int64_t)tid * nb]));
+    const int64_t r0 = (int64_t)blockIdx.x * P.X.chunk;
+    const int64_t r1 = r0 + P.X.chunk < P.X.rows ? r0 + P.X.chunk : P.X.rows;
+    constexpr int IPT = GSQL_MAX_RANKS * PUSH_CELLS / PUSH_THREADS;  // cells per thread in the scan
+    for (int64_t t0 = r0; t0 < r1; t0 += PUSH_TILE) {
+        const int n_tile = (int)(r1 - t0 < PUSH_TILE ? r1 - t0 : PUSH_TILE);
+        for (int i = tid; i < R * PUSH_CELLS; i += PUSH_THREADS) cell[i] = 0;
+        __syncthreads();  // also orders the previous tile's last flush / cur update before this tile's writes
+        // 1. destination of this thread's rows and their rank among the warp's rows with the same destination
+        int d[PUSH_RPT];
+        unsigned int rank[PUSH_RPT];
+#pragma unroll
+        for (int k = 0; k < PUSH_RPT; k++) {
+            const int64_t r = t0 + k * PUSH_THREADS + tid;
+            d[k] = r < r1 ? row_part(P.X, r) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < PUSH_RPT; k++) {
+            const unsigned peers = __match_any_sync(0xffffffffu, d[k]);
+            rank[k] = __popc(peers & ((1u << lane) - 1u));
+            if (d[k] >= 0 && rank[k] == 0) cell[d[k] * PUSH_CELLS + warp * PUSH_RPT + k] = __popc(peers);
+        }
+        __syncthreads();
+        {  // 2. exclusive scan of the cells in (dst, warp, slot) order: a destination's rows become one run of the tile
+            unsigned int v[IPT];
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const int c = tid * IPT + i;
+                v[i] = c < R * PUSH_CELLS ? cell[c] : 0;
+            }
+            BlockScan(scan_tmp).ExclusiveSum(v, v);
+#pragma unroll
+            for (int i = 0; i < IPT; i++) {
+                const int c = tid * IPT + i;
+                if (c < R * PUSH_CELLS) {
+                    cell[c] = v[i];
+                    if (c % PUSH_CELLS == 0) dstart[c / PUSH_CELLS] = v[i];
+                }
+            }
+            if (tid == 0) dstart[R] = (unsigned int)n_tile;
+        }
+        __syncthreads();
+        unsigned int pos[PUSH_RPT];
+#pragma unroll
+        for (int k = 0; k < PUSH_RPT; k++) {
+            pos[k] = 0;
+            if (d[k] >= 0) {
+                pos[k] = cell[d[k] * PUSH_CELLS + warp * PUSH_RPT + k] + rank[k];
+                sdest[pos[k]] = (unsigned char)d[k];
+            }
+        }
+        // 3. column after column: stage in destination order, then consecutive threads store consecutive elements of a
+        //    destination's run into that GPU's receive buffer
+        int phase = 0;
+#pragma unroll 1
+        for (int c = 0; c < P.X.in.n; c++) {
+            const DCol &col = P.X.in.c[c];
+            const bool is32 = col.type == GSQL_T_INT32;
+            unsigned long long v[PUSH_RPT];
+#pragma unroll
+            for (int k = 0; k < PUSH_RPT; k++) {
+                const int64_t r = t0 + k * PUSH_THREADS + tid;
+                v[k] = 0;
+                if (d[k] >= 0) v[k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
+                                           : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+            }
+            unsigned long long *st = stage[phase];
+#pragma unroll
+            for (int k = 0; k < PUSH_RPT; k++)
+                if (d[k] >= 0) st[pos[k]] = v[k];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < PUSH_RPT; k++) {
+                const int i = k * PUSH_THREADS + tid;
+                if (i < n_tile) {
+                    const int dd = sdest[i];
+                    const unsigned long long row = cur[dd] + (unsigned)(i - (int)dstart[dd]);
+                    char *dst = P.peer_base[dd] + P.col_off[c];
+                    if (is32) reinterpret_cast<int *>(dst)[row] = (int)(unsigned)st[i];
+                    else reinterpret_cast<long long *>(dst)[row] = (long long)st[i];
+                }
+            }
+            phase ^= 1;
+            if (P.null_off[c] >= 0) {  // NULL bytes travel the same way
+                unsigned long long *sn = stage[phase];
+#pragma unroll
+                for (int k = 0; k < PUSH_RPT; k++) {
+                    const int64_t r = t0 + k * PUSH_THREADS + tid;
+                    if (d[k] >= 0) sn[pos[k]] = col.nulls ? (unsigned long long)col.nulls[r] : 0ULL;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < PUSH_RPT; k++) {
+                    const int i = k * PUSH_THREADS + tid;
+                    if (i < n_tile) {
+                        const int dd = sdest[i];
+                        const unsigned long long row = cur[dd] + (unsigned)(i - (int)dstart[dd]);
+                        reinterpret_cast<uint8_t *>(P.peer_base[dd] + P.null_off[c])[row] = (uint8_t)sn[i];
+                    }
+                }
+                phase ^= 1;
+            }
+        }
+        __syncthreads();
+        if (tid < R) cur[tid] += dstart[tid + 1] - dstart[tid];
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t gsql_xchg_plan_layout(int32_t nranks, int32_t nslabs, int32_t me, const int64_t *matrix, int64_t *send_base,
+                                         int64_t *recv_base, int64_t *slab_rows) {
+    if (nranks < 1 || nslabs < 1 || me < 0 || me >= nranks || !matrix) return -1;
+    auto m_at = [&](int src, int slab, int dst) -> int64_t { return matrix[((size_t)src * nslabs + slab) * nranks + dst]; };
+    int64_t worst = 0;
+    for (int dst = 0; dst < nranks; dst++) {
+        int64_t row = 0;  // dst's buffer: slab after slab; inside a slab, source after source
+        for (int slab = 0; slab < nslabs; slab++) {
+            const int64_t slab_first = row;
+            for (int src = 0; src < nranks; src++) {
+                if (src == me && send_base) send_base[(size_t)slab * nranks + dst] = row;
+                if (dst == me && recv_base) recv_base[(size_t)slab * nranks + src] = row;
+                row += m_at(src, slab, dst);
+            }
+            if (dst == me && slab_rows) slab_rows[slab] = row - slab_first;
+        }
+        if (row > worst) worst = row;
+    }
+    return worst;
+}
+
+static void p2p_close(gsql_xchg *x) {
+    if (!x->p2p) return;
+    gsql_ctx *ctx = x->ctx;
+    if (x->pstream) cudaStreamSynchronize(x->pstream);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->nranks; r++)
+        if (r != ctx->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+    if (x->base) cudaFree(x->base);
+    if (x->in_ev) cudaEventDestroy(x->in_ev);
+    for (int i = 0; i < GSQL_MAX_SLABS; i++)
+        if (x->slab_ev[i]) cudaEventDestroy(x->slab_ev[i]);
+    if (x->pstream) cudaStreamDestroy(x->pstream);
+    if (x->host_matrix) cudaFreeHost(x->host_matrix);
+    if (x->host_err) cudaFreeHost(x->host_err);
+    x->p2p = false;
+    x->base = nullptr;
+}
+
+extern "C" gsql_status gsql_xchg_open_p2p(gsql_xchg *x, int64_t recv_capacity_rows, uint32_t nullable_cols) {
+    if (!x || recv_capacity_rows < 1) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    const gsql_xchg_spec &s = x->spec;
+    const int R = ctx->nranks;
+    if (x->p2p) return gsql_set_error(ctx, GSQL_E_STATE, "exchange is already open");
+    if (R > GSQL_MAX_RANKS) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "at most %d ranks", GSQL_MAX_RANKS);
+    if (s.nparts != R) return gsql_set_error(ctx, GSQL_E_INVALID, "exchange has %d partitions but the communicator has %d ranks", s.nparts, R);
+    NcclApi *api = nccl_api();
+    if (R > 1 && (!ctx->nccl_comm || !api->ok)) return gsql_set_error(ctx, GSQL_E_STATE, "gsql_comm_init has not been called");
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    // ---- layout of the allocation: control block | column 0 | column 1 | ... | NULL bytes of the nullable columns
+    size_t off = CTRL_BYTES;
+    for (int c = 0; c < s.n_cols; c++) {
+        x->col_off[c] = (int64_t)off;
+        off += ((size_t)recv_capacity_rows * gsql_type_width(s.types[c]) + 255) & ~(size_t)255;
+    }
+    for (int c = 0; c < s.n_cols; c++) {
+        x->null_off[c] = -1;
+        if (nullable_cols & (1u << c)) {
+            x->null_off[c] = (int64_t)off;
+            off += ((size_t)recv_capacity_rows + 255) & ~(size_t)255;
+        }
+    }
+    x->alloc_bytes = off;
+    x->cap = recv_capacity_rows;
+    {
+        cudaError_t e = cudaMalloc((void **)&x->base, off);  // not from the stream-ordered pool: IPC needs a plain allocation
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            x->base = nullptr;
+            return gsql_set_error(ctx, GSQL_E_OOM, "cudaMalloc(%zu bytes) for the receive buffer: %s", off, cudaGetErrorString(e));
+        }
+    }
+    x->p2p = true;  // from here on p2p_close releases everything
+    GSQL_CUDA(ctx, cudaMemset(x->base, 0, CTRL_BYTES));
+    GSQL_CUDA(ctx, cudaDeviceSynchronize());
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    GSQL_CUDA(ctx, cudaStreamCreateWithPriority(&x->pstream, cudaStreamNonBlocking, hi));
+    GSQL_CUDA(ctx, cudaEventCreateWithFlags(&x->in_ev, cudaEventDisableTiming));
+    for (int i = 0; i < GSQL_MAX_SLABS; i++) GSQL_CUDA(ctx, cudaEventCreateWithFlags(&x->slab_ev[i], cudaEventDisableTiming));
+    GSQL_CUDA(ctx, cudaHostAlloc((void **)&x->host_matrix, sizeof(long long) * GSQL_MAX_RANKS * GSQL_MAX_SLABS * GSQL_MAX_RANKS, cudaHostAllocDefault));
+    GSQL_CUDA(ctx, cudaHostAlloc((void **)&x->host_err, 64, cudaHostAllocDefault));
+    for (int r = 0; r < GSQL_MAX_RANKS; r++) x->peer_base[r] = nullptr;
+    x->peer_base[ctx->rank] = x->base;
+    if (R > 1) {  // exchange the IPC handles (NCCL is plumbing here: 64 bytes per rank, once)
+        cudaIpcMemHandle_t mine;
+        GSQL_CUDA(ctx, cudaIpcGetMemHandle(&mine, x->base));
+        DevBuf d_mine, d_all;
+        GSQL_TRY(d_mine.alloc(ctx, sizeof(mine)));
+        GSQL_TRY(d_all.alloc(ctx, sizeof(mine) * (size_t)R));
+        GSQL_CUDA(ctx, cudaMemcpyAsync(d_mine.p, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+        GSQL_NCCL(ctx, api->AllGather(d_mine.p, d_all.p, sizeof(mine), ncclInt8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+        std::vector<cudaIpcMemHandle_t> all((size_t)R);
+        GSQL_CUDA(ctx, cudaMemcpyAsync(all.data(), d_all.p, sizeof(mine) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+        GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // every rank zeroed its control block before contributing
+        for (int r = 0; r < R; r++) {
+            if (r == ctx->rank) continue;
+            void *p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return gsql_set_error(ctx, GSQL_E_CUDA, "cudaIpcOpenMemHandle(rank %d): %s — peer access over NVLink is required", r, cudaGetErrorString(e));
+            }
+            x->peer_base[r] = (char *)p;
+        }
+    }
+    return GSQL_OK;
+}
+
+static void fill_peers(gsql_xchg *x, PeerSet *S) {
+    memset(S, 0, sizeof(*S));
+    S->nranks = x->ctx->nranks;
+    S->me = x->ctx->rank;
+    for (int r = 0; r < S->nranks; r++) S->ctrl[r] = reinterpret_cast<P2PCtrl *>(x->peer_base[r]);
+}
+
+static int push_blocks(gsql_ctx *ctx, int64_t rows) {
+    int per_sm = 2;
+    if (const char *e = getenv("GSQL_XCHG_PUSH_CTAS_PER_SM")) per_sm = atoi(e);
+    if (per_sm < 1) per_sm = 1;
+    int64_t nb = (int64_t)ctx->sm_count * per_sm;
+    if (const char *e = getenv("GSQL_XCHG_PUSH_CTAS")) nb = atoll(e);  // fewer CTAs leave more of the GPU to the overlapped consumer
+    int64_t tiles = div_up(rows > 0 ? rows : 1, PUSH_TILE);
+    if (nb > tiles) nb = tiles;
+    if (nb < 1) nb = 1;
+    return (int)nb;
+}
+
+extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_t nslabs, int64_t *slab_rows, int64_t *total_rows) {
+    if (!x || !in) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    if (!x->p2p) return gsql_set_error(ctx, GSQL_E_STATE, "gsql_xchg_open_p2p has not been called");
+    const gsql_xchg_spec &s = x->spec;
+    GSQL_TRY(validate_batch(ctx, in, s.n_cols, s.types));
+    if (in->mem != GSQL_MEM_DEVICE) return gsql_set_error(ctx, GSQL_E_INVALID, "push works on device-resident batches");
+    if (nslabs < 1 || nslabs > GSQL_MAX_SLABS) return gsql_set_error(ctx, GSQL_E_INVALID, "1..%d slabs", GSQL_MAX_SLABS);
+    for (int c = 0; c < s.n_cols; c++)
+        if (in->cols[c].nulls && x->null_off[c] < 0) return gsql_set_error(ctx, GSQL_E_INVALID, "column %d carries NULLs but the exchange was opened without a mask for it", c);
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int R = ctx->nranks, me = ctx->rank;
+    const int64_t n = in->rows;
+    StagedBatch sb;
+    GSQL_TRY(stage_batch(ctx, in, &sb));
+    // rows per slab: a multiple of the tile, the last slabs may be short or empty
+    const int64_t SR = div_up(div_up(n > 0 ? n : 1, nslabs), PUSH_TILE) * PUSH_TILE;
+    std::vector<XParams> XP((size_t)nslabs);
+    std::vector<int64_t> rows_of((size_t)nslabs, 0);
+    size_t tmp_bytes = 0;
+    bool regrow = false;
+    for (int i = 0; i < nslabs; i++) {
+        const int64_t lo = (int64_t)i * SR;
+        rows_of[(size_t)i] = lo < n ? (n - lo < SR ? n - lo : SR) : 0;
+        fill_xparams(x, sb, lo < n ? lo : 0, rows_of[(size_t)i], &XP[(size_t)i]);
+        XParams &X = XP[(size_t)i];
+        int nb = push_blocks(ctx, X.rows);
+        X.chunk = div_up(div_up(X.rows > 0 ? X.rows : 1, nb), PUSH_TILE) * PUSH_TILE;
+        nb = (int)div_up(X.rows, X.chunk);
+        X.nblocks = nb < 1 ? 1 : nb;
+        const int64_t nh = (int64_t)R * X.nblocks;
+        if (x->hist[i].bytes < (size_t)(nh + 1) * 8 || x->offs[i].bytes < (size_t)(nh + 1) * 8) regrow = true;
+        size_t tb = 0;
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tb, (int64_t *)nullptr, (int64_t *)nullptr, nh + 1, x->pstream));
+        if (tb > tmp_bytes) tmp_bytes = tb;
+    }
+    if (regrow || x->scan_tmp.bytes < tmp_bytes) {  // the scratch lives in the handle; it only grows, and never under a push in flight
+        GSQL_CUDA(ctx, cudaStreamSynchronize(x->pstream));
+        for (int i = 0; i < nslabs; i++) {
+            const int64_t nh = (int64_t)R * XP[(size_t)i].nblocks;
+            GSQL_TRY(x->hist[i].grow(ctx, (size_t)(nh + 1) * 8, 0));
+            GSQL_TRY(x->offs[i].grow(ctx, (size_t)(nh + 1) * 8, 0));
+        }
+        GSQL_TRY(x->scan_tmp.grow(ctx, tmp_bytes ? tmp_bytes : 16, 0));
+    }
+    // the exchange stream starts after everything the caller enqueued on the context stream: the input exists, and
+    // the consumers of the previous push's rows are done with the receive buffer (and so, after the publish barrier
+    // below, are the consumers on every other rank: nobody overwrites rows that are still being read)
+    GSQL_CUDA(ctx, cudaEventRecord(x->in_ev, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamWaitEvent(x->pstream, x->in_ev, 0));
+    cudaStream_t ps = x->pstream;
+    // ---- 1. histograms + scans of every slab
+    SlabOffs SO;
+    memset(&SO, 0, sizeof(SO));
+    SO.nslabs = nslabs;
+    SO.parity = (int32_t)(x->pushes & 1);
+    for (int i = 0; i < nslabs; i++) {
+        XParams &X = XP[(size_t)i];
+        const int64_t nh = (int64_t)R * X.nblocks;
+        GSQL_CUDA(ctx, cudaMemsetAsync(x->hist[i].p, 0, (size_t)(nh + 1) * 8, ps));
+        if (X.rows > 0) {
+            ctx->launches++;
+            k_xchg_hist<<<X.nblocks, XBLOCK, (size_t)R * sizeof(unsigned int), ps>>>(X, x->hist[i].as<int64_t>());
+        }
+        size_t tb = x->scan_tmp.bytes;
+        GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(x->scan_tmp.p, tb, x->hist[i].as<int64_t>(), x->offs[i].as<int64_t>(), nh + 1, ps));
+        SO.offs[i] = x->offs[i].as<int64_t>();
+        SO.nblocks[i] = X.nblocks;
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    // ---- 2. publish the counts to every peer, meet, read the whole matrix
+    PeerSet S;
+    fill_peers(x, &S);
+    ctx->launches++;
+    k_p2p_publish<<<1, 256, 0, ps>>>(S, SO, ++x->seq);
+    GSQL_CUDA(ctx, cudaGetLastError());
+    P2PCtrl *my = reinterpret_cast<P2PCtrl *>(x->base);
+    GSQL_CUDA(ctx, cudaMemcpyAsync(x->host_matrix, &my->counts[SO.parity][0][0][0], sizeof(long long) * GSQL_MAX_RANKS * GSQL_MAX_SLABS * GSQL_MAX_RANKS,
+                                   cudaMemcpyDeviceToHost, ps));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(x->host_err, &my->err, 4, cudaMemcpyDeviceToHost, ps));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ps));
+    x->pushes++;
+    if (*x->host_err) {
+        ctx->sticky = true;
+        return gsql_set_error(ctx, GSQL_E_NCCL, "peer barrier timed out: a rank did not join the push");
+    }
+    std::vector<int64_t> M((size_t)R * nslabs * R), send_base((size_t)nslabs * R), recv_base((size_t)nslabs * R);
+    for (int src = 0; src < R; src++)
+        for (int i = 0; i < nslabs; i++)
+            for (int dst = 0; dst < R; dst++)
+                M[((size_t)src * nslabs + i) * R + dst] = x->host_matrix[((size_t)src * GSQL_MAX_SLABS + i) * GSQL_MAX_RANKS + dst];
+    const int64_t worst = gsql_xchg_plan_layout(R, nslabs, me, M.data(), send_base.data(), recv_base.data(), x->slab_rows);
+    int64_t mine = 0;
+    for (int i = 0; i < nslabs; i++) {
+        x->slab_base[i] = mine;
+        mine += x->slab_rows[i];
+        if (slab_rows) slab_rows[i] = x->slab_rows[i];
+    }
+    x->last_slabs = nslabs;
+    if (worst > x->cap) {  // the same verdict on every rank (same matrix, same capacity): nobody sends
+        x->last_slabs = 0;
+        if (total_rows) *total_rows = worst;
+        return gsql_set_error(ctx, GSQL_E_CAPACITY, "push needs %lld receive rows on some rank, capacity %lld", (long long)worst, (long long)x->cap);
+    }
+    if (total_rows) *total_rows = mine;
+    // ---- 3. slab after slab: split-and-push kernel, then all ranks meet; the slab's event releases its consumer
+    for (int i = 0; i < nslabs; i++) {
+        XParams &X = XP[(size_t)i];
+        if (X.rows > 0) {
+            PushParams PP;
+            memset(&PP, 0, sizeof(PP));
+            PP.X = X;
+            PP.offs = x->offs[i].as<int64_t>();
+            for (int d = 0; d < R; d++) {
+                PP.base_row[d] = send_base[(size_t)i * R + d];
+                PP.peer_base[d] = x->peer_base[d];
+            }
+            for (int c = 0; c < s.n_cols; c++) {
+                PP.col_off[c] = x->col_off[c];
+                PP.null_off[c] = x->null_off[c];
+            }
+            ctx->launches++;
+            k_xchg_push<<<X.nblocks, PUSH_THREADS, 0, ps>>>(PP);
+            GSQL_CUDA(ctx, cudaGetLastError());
+        }
+        ctx->launches++;
+        k_p2p_barrier<<<1, 32, 0, ps>>>(S, ++x->seq);
+        GSQL_CUDA(ctx, cudaGetLastError());
+        GSQL_CUDA(ctx, cudaEventRecord(x->slab_ev[i], ps));
+    }
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_xchg_recv_view(gsql_xchg *x, int32_t slab, gsql_batch *view) {
+    if (!x || !view || !view->cols) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (!x->p2p || x->last_slabs < 1) return gsql_set_error(ctx, GSQL_E_STATE, "no push to receive from");
+    if (slab < -1 || slab >= x->last_slabs) return gsql_set_error(ctx, GSQL_E_INVALID, "slab %d of %d", slab, x->last_slabs);
+    const gsql_xchg_spec &s = x->spec;
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int last = slab < 0 ? x->last_slabs - 1 : slab;
+    GSQL_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, x->slab_ev[last], 0));
+    int64_t first = 0, rows = 0;
+    if (slab < 0) {
+        for (int i = 0; i < x->last_slabs; i++) rows += x->slab_rows[i];
+    } else {
+        first = x->slab_base[slab];
+        rows = x->slab_rows[slab];
+    }
+    view->rows = rows;
+    view->ncols = s.n_cols;
+    view->mem = GSQL_MEM_DEVICE;
+    for (int c = 0; c < s.n_cols; c++) {
+        view->cols[c].type = s.types[c];
+        view->cols[c].reserved = 0;
+        view->cols[c].data = x->base + x->col_off[c] + (size_t)first * gsql_type_width(s.types[c]);
+        view->cols[c].nulls = x->null_off[c] >= 0 ? reinterpret_cast<uint8_t *>(x->base + x->null_off[c] + first) : nullptr;
+    }
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_xchg_push_wait(gsql_xchg *x) {
+    if (!x) return GSQL_E_INVALID;
+    gsql_ctx *ctx = x->ctx;
+    if (!x->p2p) return gsql_set_error(ctx, GSQL_E_STATE, "gsql_xchg_open_p2p has not been called");
+    GSQL_CUDA(ctx, cudaStreamSynchronize(x->pstream));
+    P2PCtrl *my = reinterpret_cast<P2PCtrl *>(x->base);
+    int32_t err = 0;
+    GSQL_CUDA(ctx, cudaMemcpy(&err, &my->err, 4, cudaMemcpyDeviceToHost));
+    if (err) {
+        ctx->sticky = true;
+        return gsql_set_error(ctx, GSQL_E_NCCL, "peer barrier timed out: a rank did not finish the push");
+    }
     return GSQL_OK;
 }

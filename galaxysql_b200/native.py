@@ -125,6 +125,7 @@ _SIGS = [
     ("gsql_partition_ids", C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, C.c_int32]),
     ("gsql_join_create", C.c_int, [_P, C.POINTER(JoinSpec), C.POINTER(_P)]),
     ("gsql_join_build_consume", C.c_int, [_P, C.POINTER(Batch)]),
+    ("gsql_join_build_consume_ref", C.c_int, [_P, C.POINTER(Batch)]),
     ("gsql_join_build_finish", C.c_int, [_P]),
     ("gsql_join_info_get", C.c_int, [_P, C.POINTER(JoinInfo)]),
     ("gsql_join_output_schema", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
@@ -145,6 +146,12 @@ _SIGS = [
     ("gsql_comm_destroy", C.c_int, [_P]),
     ("gsql_xchg_all_to_all", C.c_int, [_P, C.POINTER(Batch), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_int64),
                                        C.POINTER(C.c_int64)]),
+    ("gsql_xchg_open_p2p", C.c_int, [_P, C.c_int64, C.c_uint32]),
+    ("gsql_xchg_push", C.c_int, [_P, C.POINTER(Batch), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("gsql_xchg_recv_view", C.c_int, [_P, C.c_int32, C.POINTER(Batch)]),
+    ("gsql_xchg_push_wait", C.c_int, [_P]),
+    ("gsql_xchg_plan_layout", C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("gsql_xchg_destroy", None, [_P]),
 ]
 ABI_SYMBOLS = [s[0] for s in _SIGS]

@@ -180,6 +180,11 @@ typedef struct gsql_join_info {
 gsql_status gsql_join_create(gsql_ctx *ctx, const gsql_join_spec *spec, gsql_join **out);
 /* consumeChunk on the build side: appends (copies) the batch; nothing of `batch` is referenced after return. */
 gsql_status gsql_join_build_consume(gsql_join *j, const gsql_batch *build_rows);
+/* Zero-copy variant for a device-resident build side that arrives as ONE batch (the output of an exchange or of
+ * another GPU operator): the columns are referenced, not copied — exactly the reference's ownership rule (the consumer
+ * retains consumed chunks: operator/util/ChunksIndex.java:48-51).  The batch must stay valid and unchanged until
+ * gsql_join_destroy; no other build batch may be consumed on this handle. */
+gsql_status gsql_join_build_consume_ref(gsql_join *j, const gsql_batch *build_rows);
 /* buildConsume: builds the hash table over everything consumed. */
 gsql_status gsql_join_build_finish(gsql_join *j);
 gsql_status gsql_join_info_get(gsql_join *j, gsql_join_info *info);
@@ -272,6 +277,38 @@ gsql_status gsql_comm_destroy(gsql_ctx *ctx);
  * recv_counts (host, nranks entries, may be NULL) = rows received from each source rank. */
 gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, gsql_batch *out, int64_t out_capacity,
                                  int64_t *out_rows, int64_t *recv_counts);
+
+/* ---- one-pass partition-and-push shuffle over NVLink peer memory (no staging buffer, no NCCL on the data path).
+ * Replaces mpp/operator/PartitionedOutputCollector.java:170-196 (partitionPage: per-destination page builders) +
+ * mpp/execution/buffer/PartitionedOutputBuffer.enqueue:138-175 + mpp/operator/ExchangeClient.java:372-437 (pull).
+ * Every rank owns a receive buffer (device memory mapped into all peers with CUDA IPC); a push call histograms the
+ * destination of every row (ExecUtils.partition, bit-exact), publishes the counts to all peers through a peer-mapped
+ * control block, and then ONE kernel per slab splits the rows by destination in shared memory and writes each
+ * destination's run of every column straight into that GPU's receive buffer.  The batch is cut into `nslabs` row
+ * slabs; slab k can be consumed (gsql_xchg_recv_view) while slab k+1 is still on the wire, on the exchange's own
+ * stream.  All three calls are collective: every rank calls them in the same order with the same nslabs. */
+#define GSQL_MAX_RANKS 16
+#define GSQL_MAX_SLABS 32
+/* Collective.  recv_capacity_rows: rows this rank (and every other: same value everywhere) can receive per push.
+ * nullable_cols: bit c set = column c travels with a NULL mask. */
+gsql_status gsql_xchg_open_p2p(gsql_xchg *x, int64_t recv_capacity_rows, uint32_t nullable_cols);
+/* Collective, asynchronous.  `in` is device-resident and must stay unchanged until the last slab has been waited for
+ * (gsql_xchg_recv_view) or gsql_xchg_push_wait returns.  slab_rows (host, nslabs entries) = rows this rank receives in
+ * each slab.  GSQL_E_CAPACITY (with *total_rows = the largest need of any rank) is returned on EVERY rank when any
+ * rank's buffer would overflow — nothing is sent.  A push overwrites the rows received by the previous push. */
+gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_t nslabs, int64_t *slab_rows, int64_t *total_rows);
+/* Makes the context stream wait for slab `slab` of the last push and describes it in place (zero copy): view->cols must
+ * have n_cols entries; data/nulls point into the receive buffer, rows = slab_rows[slab].  slab = -1: all slabs as one
+ * batch (they are contiguous).  The view is valid until the next push on this handle. */
+gsql_status gsql_xchg_recv_view(gsql_xchg *x, int32_t slab, gsql_batch *view);
+/* Blocks the host until every slab of the last push has been sent and received. */
+gsql_status gsql_xchg_push_wait(gsql_xchg *x);
+/* Host-side layout arithmetic of a push, exported so that it can be tested without a GPU: matrix[src][slab][dst]
+ * (nranks*nslabs*nranks entries) -> send_base[slab][dst] = first row of this rank's (slab, dst) segment inside dst's
+ * receive buffer, recv_base[slab][src] = first row of src's segment of that slab in this rank's buffer,
+ * slab_rows[slab]; returns the largest number of rows any rank receives. */
+int64_t gsql_xchg_plan_layout(int32_t nranks, int32_t nslabs, int32_t me, const int64_t *matrix, int64_t *send_base,
+                              int64_t *recv_base, int64_t *slab_rows);
 void gsql_xchg_destroy(gsql_xchg *x);
 
 #if defined(__GNUC__)

@@ -370,27 +370,118 @@ def test_partition_exchange_vs_oracle(gu, nparts, mem):
         off += exp_counts[p]
 
 
-def test_all_to_all_single_rank(gu, monkeypatch):
-    """The NCCL path with a 1-rank communicator: partition + self send/recv must return every row — through the
-    sequential path and through the opt-in slabbed pipeline (GSQL_XCHG_SLABS: 3 slabs, the last one short, NULL masks)."""
-    import torch
+def test_all_to_all_single_rank(gu):
+    """The NCCL transport with a 1-rank communicator: partition + self send/recv must return every row."""
     from galaxysql_b200 import api
     c = gu.ctx()
     api.comm_init(c, 1, 0, api.comm_unique_id())
     n = 50_000
-    cols = [((ku.rand_u64(n, 1) % np.uint64(999)).astype(np.int64), None), (np.arange(n, dtype=np.int32), None)]
+    cols = [((ku.rand_u64(n, 1) % np.uint64(999)).astype(np.int64), None), ku.with_nulls(np.arange(n, dtype=np.int32), 0.1, 9)]
     x = api.Exchange(c, [1, 0], [0], 1)
     out, recv = x.all_to_all(gu.to_device(cols), capacity=n)
     assert recv.tolist() == [n]
     assert ku.rows_multiset(gu.to_numpy(out)) == ku.rows_multiset(cols)
-    monkeypatch.setenv("GSQL_XCHG_SLABS", "3")
-    n2 = 50_001
-    cols2 = [((ku.rand_u64(n2, 2) % np.uint64(999)).astype(np.int64), None), ku.with_nulls(np.arange(n2, dtype=np.int32), 0.1, 9)]
-    out2, recv2 = x.all_to_all(gu.to_device(cols2), capacity=n2)
-    assert recv2.tolist() == [n2]
-    assert ku.rows_multiset(gu.to_numpy(out2)) == ku.rows_multiset(cols2)
-    monkeypatch.delenv("GSQL_XCHG_SLABS")
+    x.close()
     c.lib.gsql_comm_destroy(c.ptr)
+    c.nranks, c.rank = 1, 0
+
+
+@pytest.mark.parametrize("nslabs", [1, 3, 7])
+def test_push_exchange_single_rank(gu, nslabs):
+    """gsql_xchg_push with one rank (every destination is this GPU): all rows arrive exactly once, slab views are
+    contiguous pieces of the whole, NULL masks travel, ragged slab sizes (the last slabs short or empty)."""
+    from galaxysql_b200 import api, native as N
+    c = gu.ctx()
+    n = 20_001 if nslabs == 7 else 300_007
+    cols = [ku.with_nulls((ku.rand_u64(n, 11) % np.uint64(5000)).astype(np.int64), 0.02, 12),
+            (np.arange(n, dtype=np.int32), None),
+            ((ku.rand_u64(n, 13) % np.uint64(1000)).astype(np.float64) / 8.0, None)]
+    x = api.Exchange(c, [N.T_INT64, N.T_INT32, N.T_FP64], [0], 1)
+    x.open_p2p(n + 10, nullable=[0])
+    for _ in range(2):   # a second push reuses (overwrites) the receive buffer
+        slab_rows = x.push(gu.to_device(cols), nslabs)
+        assert sum(slab_rows) == n
+        whole = gu.to_numpy(x.recv(-1))
+        parts = [gu.to_numpy(x.recv(i)) for i in range(nslabs)]
+        c.sync()
+        assert [len(p[0][0]) for p in parts] == slab_rows
+        assert ku.rows_multiset(whole) == ku.rows_multiset(cols)
+        cat = [(np.concatenate([p[k][0] for p in parts]), None if whole[k][1] is None else np.concatenate([p[k][1] for p in parts])) for k in range(3)]
+        for k in range(3):
+            assert np.array_equal(cat[k][0], whole[k][0])
+    # empty input, and a too-small buffer
+    assert x.push(gu.to_device([(c_[0][:0], None if c_[1] is None else c_[1][:0]) for c_ in cols]), 2) == [0, 0]
+    x.close()
+    small = api.Exchange(c, [N.T_INT64], [0], 1)
+    small.open_p2p(100)
+    with pytest.raises(N.CapacityError):
+        small.push(gu.to_device([(cols[0][0], None)]), 1)
+    small.close()
+
+
+def test_join_all_zero_null_masks_keep_the_fast_path(gu, small_partitions):
+    """A caller that always hands over isNull[] arrays (the JNI shim) must still reach the packed-row fast path when no
+    row is NULL: masks are reduced once on the device and dropped when all-zero — on both sides, host and device."""
+    from galaxysql_b200 import api, native as N
+    outer, inner, kc = _unique_key_tables(40_000, 1_100_000, 60_000, np.int64, 2, 2, seed=91)
+    spec = orc.JoinSpec(orc.JOIN_INNER, [kc], [0], [orc.T_INT64])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    zmask = lambda cols: [(d, np.zeros(len(d), dtype=bool)) for d, _ in cols]
+    for mem in ("host", "device"):
+        j = api.HashJoin(gu.ctx(), N.JOIN_INNER, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+        b = zmask(inner)
+        j.build_consume(gu.to_device(b) if mem == "device" else b)
+        j.build_finish()
+        assert j.info().fast_path == 1
+        gu.ctx().profile(True)
+        gu.ctx().profile_reset()
+        p = zmask(outer)
+        got = gu.to_numpy(j.probe(gu.to_device(p) if mem == "device" else p))
+        prof = gu.ctx().profile_dump()
+        gu.ctx().profile(False)
+        assert "join_fast_probe" in prof and "join_probe_count" not in prof, prof   # the packed-row kernels ran, not the two-pass path
+        assert ku.rows_multiset([(d, None) for d, _ in got]) == exp
+        j.close()
+
+
+def test_join_build_consume_ref_is_zero_copy_and_equal(gu, small_partitions):
+    import torch
+    from galaxysql_b200 import api, native as N
+    outer, inner, kc = _unique_key_tables(40_000, 150_000, 60_000, np.int64, 2, 2, seed=93)
+    spec = orc.JoinSpec(orc.JOIN_LEFT, [kc], [0], [orc.T_INT64])
+    exp = ku.rows_multiset(orc.hash_join(spec, outer, inner))
+    j = api.HashJoin(gu.ctx(), N.JOIN_LEFT, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    dev_inner = gu.to_device(inner)
+    before = torch.cuda.memory_allocated()
+    j.build_consume_ref(dev_inner)
+    with pytest.raises(N.GsqlError):
+        j.build_consume(dev_inner)           # the referenced batch is the whole build side
+    j.build_finish()
+    assert j.info().fast_path == 1
+    assert ku.rows_multiset(gu.to_numpy(j.probe(gu.to_device(outer)))) == exp
+    assert torch.cuda.memory_allocated() <= before + (1 << 20)
+    j.close()
+    # duplicates: the referenced columns feed the generic chained table as well
+    inner_d = [(np.concatenate([c[0], c[0][:100]]), None) for c in inner]
+    j = api.HashJoin(gu.ctx(), N.JOIN_INNER, gu._types(outer), gu._types(inner), [kc], [0], [N.T_INT64])
+    j.build_consume_ref(gu.to_device(inner_d))
+    j.build_finish()
+    spec = orc.JoinSpec(orc.JOIN_INNER, [kc], [0], [orc.T_INT64])
+    assert ku.rows_multiset(gu.to_numpy(j.probe(gu.to_device(outer)))) == ku.rows_multiset(orc.hash_join(spec, outer, inner_d))
+    j.close()
+
+
+def test_agg_many_small_batches_clustered_high_cardinality(gu):
+    """Keys arrive clustered (~16 rows per group, groups never repeat across batches): every batch adds tens of thousands
+    of new groups through the privatised kernels' merges, which ignore the capacity check — the table must grow between
+    launches instead of running past its arrays (round-1 advisor finding)."""
+    n, per = 4_000_000, 16
+    k = (np.arange(n, dtype=np.int64) // per) * 7919 + 3
+    v = (ku.rand_u64(n, 21) % np.uint64(1000)).astype(np.float64)
+    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1])]
+    exp = orc.hash_agg([(k, None), (v, None)], [0], aggs, 8)
+    got = gu.gpu_hash_agg([(k, None), (v, None)], [0], aggs, 8, mem="device", batches=40)
+    gu.approx_rows_equal(got, exp, float_cols=[2], key_cols=[0], rtol=RTOL)
 
 
 # ------------------------------------------------------------------------------------------------ low-cardinality / fused Q1 shape
