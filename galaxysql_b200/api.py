@@ -423,13 +423,120 @@ class HashAgg:
             _alloc_out(self.ctx, self.out_types, 1, mem, [True] * len(self.out_types)), 0)
 
 
+class E:
+    """Expression builder for Scan: E.col(i), E.lit(v) and Python operators -> a postfix program (gsql_expr).
+    `&`, `|`, `~` are SQL AND / OR / NOT; comparisons yield BIGINT 0/1; `/` is DOUBLE division."""
+
+    def __init__(self, ins):
+        self.ins = ins  # list of (op, arg, const)
+
+    @staticmethod
+    def col(i: int) -> "E":
+        return E([(N.OP_COL, i, 0)])
+
+    @staticmethod
+    def lit(v) -> "E":
+        if isinstance(v, float):
+            return E([(N.OP_CONST_F64, 0, float(v))])
+        return E([(N.OP_CONST_I64, 0, int(v))])
+
+    @staticmethod
+    def _wrap(v) -> "E":
+        return v if isinstance(v, E) else E.lit(v)
+
+    def _bin(self, other, op, swap=False):
+        o = E._wrap(other)
+        a, b = (o, self) if swap else (self, o)
+        return E(a.ins + b.ins + [(op, 0, 0)])
+
+    def __add__(self, o): return self._bin(o, N.OP_ADD)
+    def __radd__(self, o): return self._bin(o, N.OP_ADD, True)
+    def __sub__(self, o): return self._bin(o, N.OP_SUB)
+    def __rsub__(self, o): return self._bin(o, N.OP_SUB, True)
+    def __mul__(self, o): return self._bin(o, N.OP_MUL)
+    def __rmul__(self, o): return self._bin(o, N.OP_MUL, True)
+    def __truediv__(self, o): return self._bin(o, N.OP_DIV)
+    def __rtruediv__(self, o): return self._bin(o, N.OP_DIV, True)
+    def __lt__(self, o): return self._bin(o, N.OP_LT)
+    def __le__(self, o): return self._bin(o, N.OP_LE)
+    def __gt__(self, o): return self._bin(o, N.OP_GT)
+    def __ge__(self, o): return self._bin(o, N.OP_GE)
+    def eq(self, o): return self._bin(o, N.OP_EQ)
+    def ne(self, o): return self._bin(o, N.OP_NE)
+    def __and__(self, o): return self._bin(o, N.OP_AND)
+    def __or__(self, o): return self._bin(o, N.OP_OR)
+    def __invert__(self): return E(self.ins + [(N.OP_NOT, 0, 0)])
+    def __neg__(self): return E(self.ins + [(N.OP_NEG, 0, 0)])
+    def is_null(self): return E(self.ins + [(N.OP_IS_NULL, 0, 0)])
+    def to_f64(self): return E(self.ins + [(N.OP_CAST_F64, 0, 0)])
+    def to_i64(self): return E(self.ins + [(N.OP_CAST_I64, 0, 0)])
+
+    def fill(self, dst: "N.Expr"):
+        if len(self.ins) > N.MAX_EXPR_INS:
+            raise ValueError("expression too long")
+        dst.n = len(self.ins)
+        for i, (op, arg, k) in enumerate(self.ins):
+            dst.ins[i].op, dst.ins[i].arg = op, arg
+            if op == N.OP_CONST_F64:
+                dst.ins[i].k.d = k
+            else:
+                dst.ins[i].k.i = k
+
+
+class Scan:
+    """gsql_scan handle: vectorised Filter + Project in one pass (VectorizedFilterExec / VectorizedProjectExec)."""
+
+    def __init__(self, ctx: Context, input_types: Sequence[int], outputs: Sequence["E"], filter: Optional["E"] = None):
+        self.ctx = ctx
+        s = N.ScanSpec()
+        s.n_input_cols = len(input_types)
+        for i, t in enumerate(input_types):
+            s.input_types[i] = t
+        s.has_filter = int(filter is not None)
+        if filter is not None:
+            filter.fill(s.filter)
+        s.n_out = len(outputs)
+        for i, e in enumerate(outputs):
+            E._wrap(e).fill(s.out[i])
+        h = C.c_void_p()
+        ctx.check(ctx.lib.gsql_scan_create(ctx.ptr, C.byref(s), C.byref(h)))
+        self.h = h
+        n = C.c_int32()
+        types = (C.c_int32 * N.MAX_SCAN_OUT)()
+        ctx.check(ctx.lib.gsql_scan_output_schema(self.h, C.byref(n), types))
+        self.out_types = [types[i] for i in range(n.value)]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gsql_scan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, cols, nullable_out: bool = True, out_cols=None):
+        """-> surviving rows as (values, nulls) columns in the input's memory space (trimmed views of out_cols)."""
+        bv = _BatchView(cols)
+        cap = max(bv.rows, 1)
+        out = out_cols if out_cols is not None else _alloc_out(self.ctx, self.out_types, cap, bv.mem, [nullable_out] * len(self.out_types))
+        ob, _keep = _out_batch(out, self.out_types, 0, bv.mem)
+        n = C.c_int64()
+        st = self.ctx.lib.gsql_scan_apply(self.h, bv.ref(), C.byref(ob), cap if out_cols is None else int(out[0][0].shape[0]), C.byref(n))
+        self.ctx.check(st, n.value)
+        return _trim(out, n.value)
+
+
 class Exchange:
     """gsql_xchg handle: hash-partition exchange (local partition, or AllToAll across ranks)."""
 
     def __init__(self, ctx: Context, types: Sequence[int], channels: Sequence[int], nparts: int,
-                 key_types: Optional[Sequence[int]] = None):
+                 key_types: Optional[Sequence[int]] = None, mode: int = 0):
         self.ctx = ctx
         s = N.XchgSpec()
+        s.mode = mode
         s.n_cols = len(types)
         for i, t in enumerate(types):
             s.types[i] = t

@@ -266,6 +266,11 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     case GSQL_AGG_SUM0:
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, c, r));
         return;
+    case GSQL_AGG_AVG_MERGE:  // (partial sum, partial count): the sum is NULL exactly when its count is 0
+        atomicAdd(&a.d[gid], val_f64(P, c, r));
+        if (!val_null(P, a.cols[1], r)) atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, a.cols[1], r));
+        a.has[gid] = 1;
+        return;
     case GSQL_AGG_MIN:
     case GSQL_AGG_MAX: {
         bool mx = a.kind == GSQL_AGG_MAX;
@@ -443,6 +448,7 @@ __global__ void __launch_bounds__(256) k_agg_finalize(const __grid_constant__ Fi
                     reinterpret_cast<int64_t *>(o.data)[2 * g + 1] = ag.has[g] ? ag.hi[g] : 0;
                 }
                 break;
+            case GSQL_AGG_AVG_MERGE:
             case GSQL_AGG_AVG: {  // sum / (double) count; NULL when no value (SpecificType2DoubleAvgV2.java:70-84)
                 bool ok = ag.has[g] && ag.l[g] != 0;
                 o.nulls[g] = ok ? 0 : 1;
@@ -473,7 +479,7 @@ int agg_out_type(int kind, int in_type) {
     switch (kind) {
     case GSQL_AGG_COUNT_STAR: case GSQL_AGG_COUNT: case GSQL_AGG_SUM0: return GSQL_T_INT64;
     case GSQL_AGG_SUM: return in_type == GSQL_T_FP64 ? GSQL_T_FP64 : GSQL_T_DEC128;
-    case GSQL_AGG_AVG: return GSQL_T_FP64;
+    case GSQL_AGG_AVG: case GSQL_AGG_AVG_MERGE: return GSQL_T_FP64;
     default: return in_type;
     }
 }
@@ -546,7 +552,7 @@ static gsql_status agg_resize(gsql_agg *a, int64_t gcap, int64_t keep) {
             GSQL_TRY(a->shi[i].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
             GSQL_CUDA(ctx, cudaMemsetAsync((char *)a->shi[i].p + keep * 8, 0, (size_t)(garr - keep) * 8, ctx->stream));
         }
-        if ((kind == GSQL_AGG_SUM && a->in_type[i] == GSQL_T_FP64) || kind == GSQL_AGG_AVG) {
+        if ((kind == GSQL_AGG_SUM && a->in_type[i] == GSQL_T_FP64) || kind == GSQL_AGG_AVG || kind == GSQL_AGG_AVG_MERGE) {
             GSQL_TRY(a->sd[i].grow(ctx, (size_t)garr * 8, (size_t)keep * 8));
             GSQL_CUDA(ctx, cudaMemsetAsync((char *)a->sd[i].p + keep * 8, 0, (size_t)(garr - keep) * 8, ctx->stream));
         }
@@ -636,15 +642,17 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     for (int k = 0; k < s.ngroups; k++) a->out_types[a->nout++] = s.input_types[s.groups[k]];
     for (int i = 0; i < s.naggs; i++) {
         const gsql_agg_call &c = s.aggs[i];
-        if (c.kind < GSQL_AGG_COUNT_STAR || c.kind > GSQL_AGG_SUM0) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "agg kind %d", c.kind); }
+        if (c.kind < GSQL_AGG_COUNT_STAR || c.kind > GSQL_AGG_AVG_MERGE) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "agg kind %d", c.kind); }
         int need = c.kind == GSQL_AGG_COUNT_STAR ? 0 : 1;
-        if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != 1)) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
+        if (c.kind == GSQL_AGG_AVG_MERGE) need = 2;
+        if (c.ncols < need || c.ncols > 4 || (c.kind != GSQL_AGG_COUNT && c.kind != GSQL_AGG_COUNT_STAR && c.ncols != need)) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: argument count", i); }
         for (int q = 0; q < c.ncols; q++)
             if (c.cols[q] < 0 || c.cols[q] >= s.n_input_cols + s.n_derived) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: column out of range", i); }
         if (c.filter_arg >= s.n_input_cols) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_INVALID, "agg %d: filter column", i); }
         a->in_type[i] = c.ncols > 0 ? (c.cols[0] < s.n_input_cols ? s.input_types[c.cols[0]] : GSQL_T_FP64) : GSQL_T_INT64;
         // planner-time fall-through cases (the stock HashAggExec keeps them): AVG over integers is DECIMAL division
         if (c.kind == GSQL_AGG_AVG && a->in_type[i] != GSQL_T_FP64) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG(integer) -> DECIMAL not on the GPU path"); }
+        if (c.kind == GSQL_AGG_AVG_MERGE && (a->in_type[i] != GSQL_T_FP64 || c.cols[1] >= s.n_input_cols || s.input_types[c.cols[1]] != GSQL_T_INT64)) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "AVG_MERGE needs (DOUBLE partial sum, BIGINT partial count)"); }
         if (c.kind == GSQL_AGG_SUM0 && a->in_type[i] != GSQL_T_INT64) { delete a; gsql_ctx_release(ctx); return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "SUM0 needs BIGINT input"); }
         a->out_types[a->nout++] = agg_out_type(c.kind, a->in_type[i]);
     }
@@ -652,6 +660,11 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     agg_fast_plan(&a->fast, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     if (s.expected_groups > (1 << 16)) a->fast.enabled = false;  // the planner expects far more groups than warp tables hold
     agg_lane_check(&a->lane, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    for (int i = 0; i < s.naggs; i++)
+        if (s.aggs[i].kind == GSQL_AGG_AVG_MERGE) {  // the privatised kernels do not know the two-column merge
+            a->fast.eligible = a->fast.enabled = false;
+            a->lane.shape_ok = a->lane.enabled = false;
+        }
     if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
     if ((getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) || (getenv("GSQL_AGG_NO_LANE") && atoi(getenv("GSQL_AGG_NO_LANE"))))
         a->lane.shape_ok = a->lane.enabled = false;

@@ -1,0 +1,392 @@
+// scan.cu — vectorised Filter + Project behind gsql_scan_* (SURVEY §8f rank 1).
+//
+// Reference path replaced (EX/ = polardbx-executor/src/main/java/com/alibaba/polardbx/executor/):
+//   EX/operator/VectorizedFilterExec.java (condition.eval -> selection array -> compacted chunk)
+//   EX/operator/VectorizedProjectExec.java:40-143 (one VectorizedExpression per output column, evaluated per chunk)
+//   EX/vectorized/** (the per-type expression classes: arithmetic, comparison, logic over Blocks with isNull[])
+// B200 shape: ONE pass.  A block takes 1024-row tiles; every thread evaluates the filter program for its rows on a
+// small typed stack (the program is uniform across threads: no divergence except NULL handling), the tile's
+// survivors are ranked with warp ballots, one global cursor bump reserves their output range, and each survivor
+// evaluates the output programs and writes its row.  Input columns are read once, surviving rows written once: the
+// kernel is HBM-bound (input bytes + selectivity x output bytes); the interpreter costs ~10 warp-instructions per
+// program step per 32 rows, far below the memory time.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int SC_THREADS = 256;
+constexpr int SC_RPT = 4;
+constexpr int SC_TILE = SC_THREADS * SC_RPT;
+
+struct DIns {        // device form of one instruction: operand types resolved on the host
+    int16_t op;
+    int8_t af, bf;   // operand a / b is a double (b = top of stack)
+    int32_t arg;
+    long long k;
+};
+struct DExpr {
+    int32_t n, out_type;  // out_type: gsql_type of the result
+    DIns ins[GSQL_MAX_EXPR_INS];
+};
+struct ScanDev {
+    int32_t has_filter, n_out;
+    DExpr filter;
+    DExpr out[GSQL_MAX_SCAN_OUT];
+};
+struct ScanOut {
+    void *data[GSQL_MAX_SCAN_OUT];
+    uint8_t *nulls[GSQL_MAX_SCAN_OUT];
+};
+
+__device__ __forceinline__ double as_f(long long v, bool is_f) { return is_f ? __longlong_as_double(v) : (double)v; }
+
+// Java (long) d: truncation toward zero, saturating, NaN -> 0
+__device__ __forceinline__ long long java_d2l(double d) {
+    if (d != d) return 0;
+    if (d >= 9223372036854775807.0) return 0x7fffffffffffffffLL;
+    if (d <= -9223372036854775808.0) return (long long)0x8000000000000000ULL;
+    return (long long)d;
+}
+
+// Evaluates one program for row r.  Returns the value (integer, or double bits when E.out_type == FP64).
+__device__ __forceinline__ long long eval_expr(const DExpr &E, const DColSet &in, int64_t r, bool &isnull) {
+    long long st[GSQL_MAX_EXPR_STACK];
+    bool nl[GSQL_MAX_EXPR_STACK];
+    int sp = 0;
+#pragma unroll 1
+    for (int i = 0; i < E.n; i++) {
+        const DIns I = E.ins[i];
+        switch (I.op) {
+        case GSQL_OP_COL: {
+            const DCol &c = in.c[I.arg];
+            const bool n = c.nulls != nullptr && c.nulls[r] != 0;
+            long long v = 0;
+            if (!n) {
+                if (c.type == GSQL_T_INT32) v = (long long)ld_stream_4(reinterpret_cast<const int *>(c.data) + r);
+                else v = ld_stream_8(reinterpret_cast<const long long *>(c.data) + r);
+            }
+            st[sp] = v; nl[sp] = n; sp++;
+            break;
+        }
+        case GSQL_OP_CONST_I64:
+        case GSQL_OP_CONST_F64:
+            st[sp] = I.k; nl[sp] = false; sp++;
+            break;
+        case GSQL_OP_NEG:
+            st[sp - 1] = I.af ? __double_as_longlong(-__longlong_as_double(st[sp - 1])) : (long long)(0ULL - (unsigned long long)st[sp - 1]);
+            break;
+        case GSQL_OP_NOT:
+            st[sp - 1] = st[sp - 1] == 0 ? 1 : 0;
+            break;
+        case GSQL_OP_IS_NULL:
+            st[sp - 1] = nl[sp - 1] ? 1 : 0;
+            nl[sp - 1] = false;
+            break;
+        case GSQL_OP_CAST_F64:
+            if (!I.af) st[sp - 1] = __double_as_longlong((double)st[sp - 1]);
+            break;
+        case GSQL_OP_CAST_I64:
+            if (I.af) st[sp - 1] = java_d2l(__longlong_as_double(st[sp - 1]));
+            break;
+        case GSQL_OP_AND:
+        case GSQL_OP_OR: {  // SQL three-valued logic
+            const long long b = st[sp - 1], a = st[sp - 2];
+            const bool bn = nl[sp - 1], an = nl[sp - 2];
+            sp--;
+            if (I.op == GSQL_OP_AND) {
+                const bool f = (!an && a == 0) || (!bn && b == 0);
+                st[sp - 1] = f ? 0 : 1;
+                nl[sp - 1] = !f && (an || bn);
+            } else {
+                const bool t = (!an && a != 0) || (!bn && b != 0);
+                st[sp - 1] = t ? 1 : 0;
+                nl[sp - 1] = !t && (an || bn);
+            }
+            break;
+        }
+        default: {  // binary arithmetic / comparison
+            const long long b = st[sp - 1], a = st[sp - 2];
+            const bool n = nl[sp - 1] || nl[sp - 2];
+            sp--;
+            nl[sp - 1] = n;
+            const bool fl = I.af || I.bf || I.op == GSQL_OP_DIV;
+            long long res = 0;
+            if (fl) {
+                const double x = as_f(a, I.af), y = as_f(b, I.bf);
+                switch (I.op) {
+                case GSQL_OP_ADD: res = __double_as_longlong(x + y); break;
+                case GSQL_OP_SUB: res = __double_as_longlong(x - y); break;
+                case GSQL_OP_MUL: res = __double_as_longlong(x * y); break;
+                case GSQL_OP_DIV: res = __double_as_longlong(x / y); break;
+                case GSQL_OP_LT: res = x < y; break;
+                case GSQL_OP_LE: res = x <= y; break;
+                case GSQL_OP_GT: res = x > y; break;
+                case GSQL_OP_GE: res = x >= y; break;
+                case GSQL_OP_EQ: res = x == y; break;
+                default: res = x != y; break;
+                }
+            } else {
+                switch (I.op) {
+                case GSQL_OP_ADD: res = (long long)((unsigned long long)a + (unsigned long long)b); break;
+                case GSQL_OP_SUB: res = (long long)((unsigned long long)a - (unsigned long long)b); break;
+                case GSQL_OP_MUL: res = (long long)((unsigned long long)a * (unsigned long long)b); break;
+                case GSQL_OP_LT: res = a < b; break;
+                case GSQL_OP_LE: res = a <= b; break;
+                case GSQL_OP_GT: res = a > b; break;
+                case GSQL_OP_GE: res = a >= b; break;
+                case GSQL_OP_EQ: res = a == b; break;
+                default: res = a != b; break;
+                }
+            }
+            st[sp - 1] = n ? 0 : res;
+            break;
+        }
+        }
+    }
+    isnull = nl[0];
+    return st[0];
+}
+
+__global__ void __launch_bounds__(SC_THREADS) k_scan(const ScanDev *__restrict__ S, const __grid_constant__ DColSet in, int64_t rows,
+                                                     const __grid_constant__ ScanOut O, unsigned long long *cursor, int32_t *flags) {
+    __shared__ unsigned int wcount[SC_THREADS / 32][SC_RPT];
+    __shared__ unsigned long long tile_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ntiles = (rows + SC_TILE - 1) / SC_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t t0 = tile * SC_TILE;
+        bool pass[SC_RPT];
+        unsigned int ballot[SC_RPT];
+#pragma unroll
+        for (int k = 0; k < SC_RPT; k++) {
+            const int64_t r = t0 + k * SC_THREADS + threadIdx.x;
+            pass[k] = r < rows;
+            if (pass[k] && S->has_filter) {
+                bool n;
+                const long long v = eval_expr(S->filter, in, r, n);
+                pass[k] = !n && v != 0;
+            }
+            ballot[k] = __ballot_sync(0xffffffffu, pass[k]);
+            if (lane == 0) wcount[warp][k] = __popc(ballot[k]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // 32 cells: exclusive scan in (slot k, warp) order keeps the tile's rows in input order
+            unsigned int acc = 0;
+            for (int k = 0; k < SC_RPT; k++)
+                for (int w = 0; w < SC_THREADS / 32; w++) {
+                    unsigned int c = wcount[w][k];
+                    wcount[w][k] = acc;
+                    acc += c;
+                }
+            tile_base = acc ? atomicAdd(cursor, (unsigned long long)acc) : 0ULL;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < SC_RPT; k++) {
+            if (!pass[k]) continue;
+            const int64_t r = t0 + k * SC_THREADS + threadIdx.x;
+            const unsigned long long pos = tile_base + wcount[warp][k] + __popc(ballot[k] & ((1u << lane) - 1u));
+            for (int e = 0; e < S->n_out; e++) {
+                bool n;
+                const long long v = eval_expr(S->out[e], in, r, n);
+                if (O.nulls[e]) O.nulls[e][pos] = n ? 1 : 0;
+                else if (n) flags[0] = 1;
+                if (S->out[e].out_type == GSQL_T_INT32) reinterpret_cast<int *>(O.data[e])[pos] = (int)v;
+                else reinterpret_cast<long long *>(O.data[e])[pos] = v;
+            }
+        }
+        __syncthreads();  // wcount / tile_base are rewritten by the next tile
+    }
+}
+
+// Host: type-checks a program, fills the device form.  Returns the result type or -1.
+int compile_expr(const gsql_expr &E, const int32_t *in_types, int n_in, DExpr *D, char *err, size_t errn) {
+    if (E.n < 1 || E.n > GSQL_MAX_EXPR_INS) { snprintf(err, errn, "program length %d", E.n); return -1; }
+    bool isf[GSQL_MAX_EXPR_STACK];
+    int sp = 0;
+    D->n = E.n;
+    for (int i = 0; i < E.n; i++) {
+        const gsql_expr_ins &I = E.ins[i];
+        DIns &d = D->ins[i];
+        d.op = (int16_t)I.op;
+        d.af = d.bf = 0;
+        d.arg = I.arg;
+        d.k = I.k.i;
+        switch (I.op) {
+        case GSQL_OP_COL:
+            if (I.arg < 0 || I.arg >= n_in) { snprintf(err, errn, "column %d out of range", I.arg); return -1; }
+            if (sp >= GSQL_MAX_EXPR_STACK) { snprintf(err, errn, "stack deeper than %d", GSQL_MAX_EXPR_STACK); return -1; }
+            isf[sp++] = in_types[I.arg] == GSQL_T_FP64;
+            break;
+        case GSQL_OP_CONST_I64:
+        case GSQL_OP_CONST_F64:
+            if (sp >= GSQL_MAX_EXPR_STACK) { snprintf(err, errn, "stack deeper than %d", GSQL_MAX_EXPR_STACK); return -1; }
+            isf[sp++] = I.op == GSQL_OP_CONST_F64;
+            break;
+        case GSQL_OP_NEG: case GSQL_OP_NOT: case GSQL_OP_IS_NULL: case GSQL_OP_CAST_F64: case GSQL_OP_CAST_I64:
+            if (sp < 1) { snprintf(err, errn, "stack underflow at %d", i); return -1; }
+            d.af = isf[sp - 1];
+            if (I.op == GSQL_OP_NOT && isf[sp - 1]) { snprintf(err, errn, "NOT over a double"); return -1; }
+            if (I.op == GSQL_OP_IS_NULL || I.op == GSQL_OP_CAST_I64 || I.op == GSQL_OP_NOT) isf[sp - 1] = false;
+            if (I.op == GSQL_OP_CAST_F64) isf[sp - 1] = true;
+            break;
+        case GSQL_OP_ADD: case GSQL_OP_SUB: case GSQL_OP_MUL: case GSQL_OP_DIV:
+        case GSQL_OP_LT: case GSQL_OP_LE: case GSQL_OP_GT: case GSQL_OP_GE: case GSQL_OP_EQ: case GSQL_OP_NE:
+        case GSQL_OP_AND: case GSQL_OP_OR:
+            if (sp < 2) { snprintf(err, errn, "stack underflow at %d", i); return -1; }
+            d.af = isf[sp - 2];
+            d.bf = isf[sp - 1];
+            if ((I.op == GSQL_OP_AND || I.op == GSQL_OP_OR) && (d.af || d.bf)) { snprintf(err, errn, "AND/OR over a double"); return -1; }
+            sp--;
+            if (I.op >= GSQL_OP_LT) isf[sp - 1] = false;                       // comparisons / logic -> BIGINT 0/1
+            else isf[sp - 1] = d.af || d.bf || I.op == GSQL_OP_DIV;
+            break;
+        default:
+            snprintf(err, errn, "unknown op %d", I.op);
+            return -1;
+        }
+    }
+    if (sp != 1) { snprintf(err, errn, "program leaves %d values", sp); return -1; }
+    int t = isf[0] ? GSQL_T_FP64 : GSQL_T_INT64;
+    if (E.n == 1 && E.ins[0].op == GSQL_OP_COL) t = in_types[E.ins[0].arg];  // pass-through keeps the column's type
+    D->out_type = t;
+    return t;
+}
+
+}  // namespace
+
+struct gsql_scan {
+    gsql_ctx *ctx;
+    gsql_scan_spec spec;
+    ScanDev host;
+    DevBuf dev, cursor, flags;
+    int32_t out_types[GSQL_MAX_SCAN_OUT];
+};
+
+extern "C" gsql_status gsql_scan_create(gsql_ctx *ctx, const gsql_scan_spec *spec, gsql_scan **out) {
+    if (!ctx || !spec || !out) return GSQL_E_INVALID;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    *out = nullptr;
+    const gsql_scan_spec &s = *spec;
+    if (s.n_input_cols < 1 || s.n_input_cols > GSQL_MAX_COLS || s.n_out < 1 || s.n_out > GSQL_MAX_SCAN_OUT)
+        return gsql_set_error(ctx, GSQL_E_INVALID, "bad scan spec sizes");
+    for (int i = 0; i < s.n_input_cols; i++)
+        if (s.input_types[i] < GSQL_T_INT32 || s.input_types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "input col %d type", i);
+    gsql_scan *sc = new gsql_scan();
+    sc->ctx = ctx;
+    sc->spec = s;
+    memset(&sc->host, 0, sizeof(sc->host));
+    char err[128] = {0};
+    sc->host.has_filter = s.has_filter != 0;
+    sc->host.n_out = s.n_out;
+    if (s.has_filter) {
+        int t = compile_expr(s.filter, s.input_types, s.n_input_cols, &sc->host.filter, err, sizeof(err));
+        if (t < 0 || t == GSQL_T_FP64) {
+            delete sc;
+            return gsql_set_error(ctx, GSQL_E_INVALID, "filter: %s", t < 0 ? err : "must be an integer / boolean expression");
+        }
+    }
+    for (int e = 0; e < s.n_out; e++) {
+        int t = compile_expr(s.out[e], s.input_types, s.n_input_cols, &sc->host.out[e], err, sizeof(err));
+        if (t < 0) { delete sc; return gsql_set_error(ctx, GSQL_E_INVALID, "output %d: %s", e, err); }
+        sc->out_types[e] = t;
+    }
+    cudaSetDevice(ctx->device);
+    gsql_status st = sc->dev.alloc(ctx, sizeof(ScanDev));
+    if (st == GSQL_OK) st = sc->cursor.alloc(ctx, 16);
+    if (st == GSQL_OK) st = sc->flags.alloc(ctx, 16);
+    if (st == GSQL_OK && cudaMemcpyAsync(sc->dev.p, &sc->host, sizeof(ScanDev), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) st = GSQL_E_CUDA;
+    if (st == GSQL_OK && cudaMemsetAsync(sc->flags.p, 0, 16, ctx->stream) != cudaSuccess) st = GSQL_E_CUDA;
+    if (st == GSQL_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) st = GSQL_E_CUDA;  // `host` may go away with the handle
+    if (st != GSQL_OK) { delete sc; return st; }
+    gsql_ctx_retain(ctx);
+    *out = sc;
+    return GSQL_OK;
+}
+
+extern "C" void gsql_scan_destroy(gsql_scan *s) {
+    if (!s) return;
+    gsql_ctx *ctx = s->ctx;
+    cudaSetDevice(ctx->device);
+    delete s;
+    if (!ctx->sticky) cudaStreamSynchronize(ctx->stream);
+    gsql_ctx_release(ctx);
+}
+
+extern "C" gsql_status gsql_scan_output_schema(gsql_scan *s, int32_t *ncols, int32_t *types) {
+    if (!s || !ncols) return GSQL_E_INVALID;
+    *ncols = s->spec.n_out;
+    if (types)
+        for (int i = 0; i < s->spec.n_out; i++) types[i] = s->out_types[i];
+    return GSQL_OK;
+}
+
+extern "C" gsql_status gsql_scan_apply(gsql_scan *s, const gsql_batch *in, gsql_batch *out, int64_t out_capacity, int64_t *out_rows) {
+    if (!s || !in || !out || !out_rows) return GSQL_E_INVALID;
+    gsql_ctx *ctx = s->ctx;
+    if (ctx->sticky) return GSQL_E_CUDA;
+    const gsql_scan_spec &sp = s->spec;
+    GSQL_TRY(validate_batch(ctx, in, sp.n_input_cols, sp.input_types));
+    GSQL_TRY(validate_batch(ctx, out, sp.n_out, s->out_types));
+    if (in->mem != out->mem) return gsql_set_error(ctx, GSQL_E_INVALID, "in and out must live in the same memory space");
+    *out_rows = 0;
+    out->rows = 0;
+    if (in->rows == 0) return GSQL_OK;
+    if (out_capacity < in->rows) {
+        *out_rows = in->rows;
+        return gsql_set_error(ctx, GSQL_E_CAPACITY, "scan output must hold the input's %lld rows", (long long)in->rows);
+    }
+    GSQL_CUDA(ctx, cudaSetDevice(ctx->device));
+    StagedBatch sb;
+    GSQL_TRY(stage_batch(ctx, in, &sb));
+    DColSet cols;
+    memset(&cols, 0, sizeof(cols));
+    cols.n = sb.ncols;
+    for (int i = 0; i < sb.ncols; i++) cols.c[i] = sb.cols[i];
+    ScanOut O;
+    memset(&O, 0, sizeof(O));
+    DevBuf odata[GSQL_MAX_SCAN_OUT], onull[GSQL_MAX_SCAN_OUT];
+    for (int e = 0; e < sp.n_out; e++) {
+        if (in->mem == GSQL_MEM_DEVICE) {
+            O.data[e] = out->cols[e].data;
+            O.nulls[e] = out->cols[e].nulls;
+        } else {
+            GSQL_TRY(odata[e].alloc(ctx, (size_t)in->rows * gsql_type_width(s->out_types[e])));
+            O.data[e] = odata[e].p;
+            if (out->cols[e].nulls) {
+                GSQL_TRY(onull[e].alloc(ctx, (size_t)in->rows));
+                O.nulls[e] = onull[e].as<uint8_t>();
+            }
+        }
+    }
+    GSQL_CUDA(ctx, cudaMemsetAsync(s->cursor.p, 0, 16, ctx->stream));
+    {
+        KernelScope ks(ctx, "scan_filter_project");
+        int64_t tiles = div_up(in->rows, SC_TILE);
+        int64_t g = tiles < (int64_t)ctx->sm_count * 8 ? tiles : (int64_t)ctx->sm_count * 8;
+        k_scan<<<(int)g, SC_THREADS, 0, ctx->stream>>>(reinterpret_cast<const ScanDev *>(s->dev.p), cols, in->rows, O, s->cursor.as<unsigned long long>(),
+                                                       s->flags.as<int32_t>());
+    }
+    GSQL_CUDA(ctx, cudaGetLastError());
+    struct { unsigned long long n; unsigned long long pad; } h;
+    int32_t hf[4];
+    GSQL_CUDA(ctx, cudaMemcpyAsync(&h, s->cursor.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaMemcpyAsync(hf, s->flags.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (hf[0]) {
+        cudaMemsetAsync(s->flags.p, 0, 16, ctx->stream);
+        return gsql_set_error(ctx, GSQL_E_INVALID, "a NULL had to be written into an output column without a nulls buffer");
+    }
+    const int64_t n = (int64_t)h.n;
+    if (in->mem == GSQL_MEM_HOST && n > 0) {
+        for (int e = 0; e < sp.n_out; e++) {
+            GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[e].data, O.data[e], (size_t)n * gsql_type_width(s->out_types[e]), cudaMemcpyDeviceToHost, ctx->stream));
+            if (out->cols[e].nulls) GSQL_CUDA(ctx, cudaMemcpyAsync(out->cols[e].nulls, O.nulls[e], (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        GSQL_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out_rows = out->rows = n;
+    return GSQL_OK;
+}

@@ -29,7 +29,8 @@ struct XParams {
     KeySet keys;
     int32_t nparts, pow2;
     int64_t rows, chunk;  // rows per block
-    int32_t nblocks, pad;
+    int32_t nblocks, mode;
+    int64_t row_base;     // index of row 0 inside the caller's batch (round-robin destinations continue across slabs)
 };
 
 struct XOut {
@@ -38,6 +39,7 @@ struct XOut {
 };
 
 __device__ __forceinline__ int row_part(const XParams &P, int64_t r) {
+    if (P.mode == GSQL_XCHG_RANDOM) return (int)((unsigned long long)(P.row_base + r) % (unsigned)P.nparts);  // RandomExchanger: balance only
     return gsql_partition_of(gsql_row_hash(P.keys, r), P.nparts, P.pow2 != 0);
 }
 
@@ -175,7 +177,8 @@ extern "C" gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spe
     if (!ctx || !spec || !out) return GSQL_E_INVALID;
     *out = nullptr;
     const gsql_xchg_spec &s = *spec;
-    if (s.n_cols < 1 || s.n_cols > GSQL_MAX_COLS || s.n_channels < 0 || s.n_channels > GSQL_MAX_KEYS || s.nparts < 1 || s.nparts > GSQL_MAX_PARTS)
+    if (s.n_cols < 1 || s.n_cols > GSQL_MAX_COLS || s.n_channels < 0 || s.n_channels > GSQL_MAX_KEYS || s.nparts < 1 || s.nparts > GSQL_MAX_PARTS ||
+        s.mode < GSQL_XCHG_HASH || s.mode > GSQL_XCHG_RANDOM)
         return gsql_set_error(ctx, GSQL_E_INVALID, "bad exchange spec");
     for (int i = 0; i < s.n_cols; i++)
         if (s.types[i] < GSQL_T_INT32 || s.types[i] > GSQL_T_FP64) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "column %d type", i);
@@ -217,6 +220,7 @@ static gsql_status partition_device(gsql_xchg *x, const StagedBatch &sb, const X
     }
     P.nparts = s.nparts;
     P.pow2 = (s.nparts & -s.nparts) == s.nparts;
+    P.mode = s.mode;
     P.rows = sb.rows;
     int nblocks = grid_rows(ctx, sb.rows, 4096, 8);
     P.chunk = div_up(sb.rows, nblocks);
@@ -264,6 +268,7 @@ extern "C" gsql_status gsql_xchg_partition(gsql_xchg *x, const gsql_batch *in, g
     GSQL_TRY(validate_batch(ctx, in, s.n_cols, s.types));
     GSQL_TRY(validate_batch(ctx, out, s.n_cols, s.types));
     if (in->mem != out->mem) return gsql_set_error(ctx, GSQL_E_INVALID, "in and out must live in the same memory space");
+    if (s.mode == GSQL_XCHG_BROADCAST) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "local broadcast: the consumers of one GPU share the device batch, nothing to partition");
     for (int p = 0; p < s.nparts; p++) part_counts[p] = 0;
     out->rows = in->rows;
     if (in->rows == 0) return GSQL_OK;
@@ -374,6 +379,8 @@ static void fill_xparams(gsql_xchg *x, const StagedBatch &sb, int64_t row0, int6
     }
     P.nparts = s.nparts;
     P.pow2 = (s.nparts & -s.nparts) == s.nparts;
+    P.mode = s.mode;
+    P.row_base = row0;
     P.rows = rows;
     int nblocks = grid_rows(x->ctx, rows, 4096, 8);
     P.chunk = div_up(rows > 0 ? rows : 1, nblocks);
@@ -392,6 +399,7 @@ extern "C" gsql_status gsql_xchg_all_to_all(gsql_xchg *x, const gsql_batch *in, 
     NcclApi *api = nccl_api();
     if (!ctx->nccl_comm || !api->ok) return gsql_set_error(ctx, GSQL_E_STATE, "gsql_comm_init has not been called");
     if (s.nparts != ctx->nranks) return gsql_set_error(ctx, GSQL_E_INVALID, "exchange has %d partitions but the communicator has %d ranks", s.nparts, ctx->nranks);
+    if (s.mode == GSQL_XCHG_BROADCAST) return gsql_set_error(ctx, GSQL_E_UNSUPPORTED, "broadcast distribution is served by gsql_xchg_push");
     GSQL_TRY(validate_batch(ctx, in, s.n_cols, s.types));
     GSQL_TRY(validate_batch(ctx, out, s.n_cols, s.types));
     if (in->mem != GSQL_MEM_DEVICE || out->mem != GSQL_MEM_DEVICE) return gsql_set_error(ctx, GSQL_E_INVALID, "all_to_all works on device-resident batches");
@@ -574,6 +582,7 @@ __device__ __forceinline__ void p2p_barrier(const PeerSet &S, unsigned long long
 
 struct SlabOffs {
     const int64_t *offs[GSQL_MAX_SLABS];  // [dst][block] exclusive scan of slab i (+ one total entry)
+    int64_t fixed[GSQL_MAX_SLABS];        // >= 0: every destination receives this many rows of slab i (broadcast)
     int32_t nblocks[GSQL_MAX_SLABS];
     int32_t nslabs, parity;
 };
@@ -584,7 +593,7 @@ __global__ void __launch_bounds__(256) k_p2p_publish(const __grid_constant__ Pee
         const int slab = i / R, dst = i % R;
         const int64_t *o = O.offs[slab];
         const int nb = O.nblocks[slab];
-        const long long cnt = (long long)(o[(int64_t)(dst + 1) * nb] - o[(int64_t)dst * nb]);
+        const long long cnt = O.fixed[slab] >= 0 ? (long long)O.fixed[slab] : (long long)(o[(int64_t)(dst + 1) * nb] - o[(int64_t)dst * nb]);
         for (int p = 0; p < R; p++) S.ctrl[p]->counts[O.parity][S.me][slab][dst] = cnt;
     }
     p2p_barrier(S, seq);
@@ -717,6 +726,32 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_cons
         }
         __syncthreads();
         if (tid < R) cur[tid] += dstart[tid + 1] - dstart[tid];
+    }
+}
+
+// distribution=broadcast: the slab's rows are read once and stored into EVERY rank's receive buffer (this rank's segment
+// of it).  Column after column, grid-stride, one element per thread: every store instruction writes a contiguous run.
+__global__ void __launch_bounds__(256) k_xchg_bcast(const __grid_constant__ PushParams P) {
+    const int R = P.X.nparts;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int c = 0; c < P.X.in.n; c++) {
+        const DCol &col = P.X.in.c[c];
+        if (col.type == GSQL_T_INT32) {
+            for (int64_t i = first; i < P.X.rows; i += stride) {
+                const int v = ld_stream_4(reinterpret_cast<const int *>(col.data) + i);
+                for (int d = 0; d < R; d++) reinterpret_cast<int *>(P.peer_base[d] + P.col_off[c])[P.base_row[d] + i] = v;
+            }
+        } else {
+            for (int64_t i = first; i < P.X.rows; i += stride) {
+                const long long v = ld_stream_8(reinterpret_cast<const long long *>(col.data) + i);
+                for (int d = 0; d < R; d++) reinterpret_cast<long long *>(P.peer_base[d] + P.col_off[c])[P.base_row[d] + i] = v;
+            }
+        }
+        if (P.null_off[c] >= 0)
+            for (int64_t i = first; i < P.X.rows; i += stride) {
+                const uint8_t v = col.nulls ? col.nulls[i] : 0;
+                for (int d = 0; d < R; d++) reinterpret_cast<uint8_t *>(P.peer_base[d] + P.null_off[c])[P.base_row[d] + i] = v;
+            }
     }
 }
 
@@ -912,6 +947,13 @@ extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_
     for (int i = 0; i < nslabs; i++) {
         XParams &X = XP[(size_t)i];
         const int64_t nh = (int64_t)R * X.nblocks;
+        SO.offs[i] = x->offs[i].as<int64_t>();
+        SO.nblocks[i] = X.nblocks;
+        SO.fixed[i] = -1;
+        if (s.mode == GSQL_XCHG_BROADCAST) {  // nothing to count: every destination receives the whole slab
+            SO.fixed[i] = X.rows;
+            continue;
+        }
         GSQL_CUDA(ctx, cudaMemsetAsync(x->hist[i].p, 0, (size_t)(nh + 1) * 8, ps));
         if (X.rows > 0) {
             ctx->launches++;
@@ -919,8 +961,6 @@ extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_
         }
         size_t tb = x->scan_tmp.bytes;
         GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(x->scan_tmp.p, tb, x->hist[i].as<int64_t>(), x->offs[i].as<int64_t>(), nh + 1, ps));
-        SO.offs[i] = x->offs[i].as<int64_t>();
-        SO.nblocks[i] = X.nblocks;
     }
     GSQL_CUDA(ctx, cudaGetLastError());
     // ---- 2. publish the counts to every peer, meet, read the whole matrix
@@ -975,7 +1015,13 @@ extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_
                 PP.null_off[c] = x->null_off[c];
             }
             ctx->launches++;
-            k_xchg_push<<<X.nblocks, PUSH_THREADS, 0, ps>>>(PP);
+            if (s.mode == GSQL_XCHG_BROADCAST) {
+                int64_t g = div_up(X.rows, 256);
+                if (g > (int64_t)ctx->sm_count * 4) g = (int64_t)ctx->sm_count * 4;
+                k_xchg_bcast<<<(int)g, 256, 0, ps>>>(PP);
+            } else {
+                k_xchg_push<<<X.nblocks, PUSH_THREADS, 0, ps>>>(PP);
+            }
             GSQL_CUDA(ctx, cudaGetLastError());
         }
         ctx->launches++;

@@ -14,7 +14,8 @@ MAX_KEYS, MAX_COLS, MAX_AGGS = 8, 32, 16
 T_INT32, T_INT64, T_FP64, T_DEC128 = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 JOIN_INNER, JOIN_LEFT, JOIN_RIGHT, JOIN_SEMI, JOIN_ANTI = 0, 1, 2, 3, 4
-AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_SUM0 = range(7)
+AGG_COUNT_STAR, AGG_COUNT, AGG_SUM, AGG_AVG, AGG_MIN, AGG_MAX, AGG_SUM0, AGG_AVG_MERGE = range(8)
+XCHG_HASH, XCHG_BROADCAST, XCHG_RANDOM = 0, 1, 2
 OK, E_INVALID, E_CUDA, E_NCCL, E_CAPACITY, E_MORE_THAN_ONE_ROW, E_UNSUPPORTED, E_STATE, E_OOM = range(9)
 
 TYPE_WIDTH = {T_INT32: 4, T_INT64: 8, T_FP64: 8, T_DEC128: 16}
@@ -95,8 +96,30 @@ class XchgSpec(C.Structure):
     _fields_ = [
         ("n_cols", C.c_int32), ("types", C.c_int32 * MAX_COLS),
         ("n_channels", C.c_int32), ("channels", C.c_int32 * MAX_KEYS), ("key_types", C.c_int32 * MAX_KEYS),
-        ("nparts", C.c_int32),
+        ("nparts", C.c_int32), ("mode", C.c_int32),
     ]
+
+
+MAX_EXPR_INS, MAX_SCAN_OUT = 24, 16
+(OP_COL, OP_CONST_I64, OP_CONST_F64, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_LT, OP_LE, OP_GT, OP_GE, OP_EQ, OP_NE,
+ OP_AND, OP_OR, OP_NOT, OP_IS_NULL, OP_CAST_F64, OP_CAST_I64) = range(1, 21)
+
+
+class _ExprK(C.Union):
+    _fields_ = [("i", C.c_int64), ("d", C.c_double)]
+
+
+class ExprIns(C.Structure):
+    _fields_ = [("op", C.c_int32), ("arg", C.c_int32), ("k", _ExprK)]
+
+
+class Expr(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("ins", ExprIns * MAX_EXPR_INS)]
+
+
+class ScanSpec(C.Structure):
+    _fields_ = [("n_input_cols", C.c_int32), ("input_types", C.c_int32 * MAX_COLS), ("has_filter", C.c_int32),
+                ("filter", Expr), ("n_out", C.c_int32), ("reserved", C.c_int32), ("out", Expr * MAX_SCAN_OUT)]
 
 
 # Every symbol include/gsql_gpu.h declares: (name, restype, argtypes).  tests/test_abi.py checks the .so exports
@@ -139,6 +162,10 @@ _SIGS = [
     ("gsql_agg_output_schema", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("gsql_agg_next", C.c_int, [_P, C.POINTER(Batch), C.c_int64, C.POINTER(C.c_int64)]),
     ("gsql_agg_destroy", None, [_P]),
+    ("gsql_scan_create", C.c_int, [_P, C.POINTER(ScanSpec), C.POINTER(_P)]),
+    ("gsql_scan_output_schema", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("gsql_scan_apply", C.c_int, [_P, C.POINTER(Batch), C.POINTER(Batch), C.c_int64, C.POINTER(C.c_int64)]),
+    ("gsql_scan_destroy", None, [_P]),
     ("gsql_xchg_create", C.c_int, [_P, C.POINTER(XchgSpec), C.POINTER(_P)]),
     ("gsql_xchg_partition", C.c_int, [_P, C.POINTER(Batch), C.POINTER(Batch), C.POINTER(C.c_int64)]),
     ("gsql_comm_unique_id", C.c_int, [C.POINTER(C.c_uint8)]),

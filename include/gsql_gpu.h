@@ -79,7 +79,10 @@ typedef enum gsql_agg_kind {
     GSQL_AGG_AVG = 3,        /* FP64 -> FP64 (Double2DoubleAvg) */
     GSQL_AGG_MIN = 4,
     GSQL_AGG_MAX = 5,
-    GSQL_AGG_SUM0 = 6        /* INT64 -> INT64 wrapping, never NULL (Long2LongSum0) */
+    GSQL_AGG_SUM0 = 6,       /* INT64 -> INT64 wrapping, never NULL (Long2LongSum0) */
+    GSQL_AGG_AVG_MERGE = 7   /* final stage of a two-phase AVG(double): cols = {partial SUM (FP64), partial COUNT (BIGINT)};
+                                result = sum of sums / (double) sum of counts, NULL when the counts add up to 0 — the
+                                global SUM + global COUNT + DIVIDE project of CBOPushAggRule.splitAgg:256-310 in one call */
 } gsql_agg_kind;
 
 /* One Block.  `nulls` == NULL means "no NULLs" (AbstractBlock.mayHaveNull() == false); otherwise one byte per
@@ -251,7 +254,62 @@ gsql_status gsql_agg_output_schema(gsql_agg *a, int32_t *ncols, int32_t *types /
 gsql_status gsql_agg_next(gsql_agg *a, gsql_batch *out, int64_t max_rows, int64_t *out_rows);
 void gsql_agg_destroy(gsql_agg *a);
 
+/* ------------------------------------------------------------------------------------------------ filter / project */
+/* Vectorised Filter + Project in one pass (replaces operator/VectorizedFilterExec.java and
+ * operator/VectorizedProjectExec.java:40-143 with the expression trees of executor/vectorized/**): rows for which the
+ * filter is TRUE (NULL and FALSE drop, as VectorizedFilterExec keeps only selected positions) are compacted and every
+ * output column is an expression over the input columns.  Expressions are postfix programs over a small typed stack:
+ * integers are 64-bit two's complement (Java long arithmetic), doubles IEEE; any NULL operand makes arithmetic and
+ * comparisons NULL; AND / OR / NOT follow SQL three-valued logic; comparisons and logic yield BIGINT 0 / 1.
+ * A program that is a single GSQL_OP_COL passes the column through with its own type. */
+typedef enum gsql_expr_op {
+    GSQL_OP_COL = 1,       /* push input column `arg` */
+    GSQL_OP_CONST_I64 = 2, /* push k.i */
+    GSQL_OP_CONST_F64 = 3, /* push k.d */
+    GSQL_OP_ADD = 4, GSQL_OP_SUB = 5, GSQL_OP_MUL = 6, GSQL_OP_DIV = 7 /* always DOUBLE */, GSQL_OP_NEG = 8,
+    GSQL_OP_LT = 9, GSQL_OP_LE = 10, GSQL_OP_GT = 11, GSQL_OP_GE = 12, GSQL_OP_EQ = 13, GSQL_OP_NE = 14,
+    GSQL_OP_AND = 15, GSQL_OP_OR = 16, GSQL_OP_NOT = 17, GSQL_OP_IS_NULL = 18,
+    GSQL_OP_CAST_F64 = 19, GSQL_OP_CAST_I64 = 20 /* (long) d, Java semantics: truncation, saturating, NaN -> 0 */
+} gsql_expr_op;
+typedef struct gsql_expr_ins {
+    int32_t op;  /* gsql_expr_op */
+    int32_t arg; /* column index for GSQL_OP_COL */
+    union { int64_t i; double d; } k;
+} gsql_expr_ins;
+#define GSQL_MAX_EXPR_INS 24
+#define GSQL_MAX_EXPR_STACK 8
+#define GSQL_MAX_SCAN_OUT 16
+typedef struct gsql_expr {
+    int32_t n;
+    int32_t reserved;
+    gsql_expr_ins ins[GSQL_MAX_EXPR_INS];
+} gsql_expr;
+typedef struct gsql_scan_spec {
+    int32_t n_input_cols;
+    int32_t input_types[GSQL_MAX_COLS];
+    int32_t has_filter;
+    gsql_expr filter;
+    int32_t n_out;
+    int32_t reserved;
+    gsql_expr out[GSQL_MAX_SCAN_OUT];
+} gsql_scan_spec;
+typedef struct gsql_scan gsql_scan;
+gsql_status gsql_scan_create(gsql_ctx *ctx, const gsql_scan_spec *spec, gsql_scan **out);
+gsql_status gsql_scan_output_schema(gsql_scan *s, int32_t *ncols, int32_t *types /* GSQL_MAX_SCAN_OUT */);
+/* nextChunk over one input batch: `out` (same mem as `in`) receives the surviving rows, at most out_capacity
+ * (GSQL_E_CAPACITY with *out_rows = in->rows otherwise: size it for the input).  An output column without a nulls
+ * buffer must not receive a NULL (GSQL_E_INVALID).  Row order across 1024-row tiles is unspecified. */
+gsql_status gsql_scan_apply(gsql_scan *s, const gsql_batch *in, gsql_batch *out, int64_t out_capacity, int64_t *out_rows);
+void gsql_scan_destroy(gsql_scan *s);
+
 /* ------------------------------------------------------------------------------------------------ exchange */
+typedef enum gsql_xchg_mode {
+    GSQL_XCHG_HASH = 0,      /* PartitioningExchanger / HashPartitionFunction: ExecUtils.partition(Chunk.hashCode(channels)) */
+    GSQL_XCHG_BROADCAST = 1, /* BroadcastExchanger / distribution=broadcast: every destination receives every row (push only;
+                                local consumers of one GPU simply share the device batch) */
+    GSQL_XCHG_RANDOM = 2     /* RandomExchanger.java:39-60: load balancing only — here round-robin by row index */
+} gsql_xchg_mode;
+
 typedef struct gsql_xchg_spec {
     int32_t n_cols;
     int32_t types[GSQL_MAX_COLS];
@@ -259,6 +317,7 @@ typedef struct gsql_xchg_spec {
     int32_t channels[GSQL_MAX_KEYS];
     int32_t key_types[GSQL_MAX_KEYS];   /* keyTargetTypes; same as column type when no conversion */
     int32_t nparts;                     /* consumers (local exchange) or ranks (remote shuffle) */
+    int32_t mode;                       /* gsql_xchg_mode */
 } gsql_xchg_spec;
 
 gsql_status gsql_xchg_create(gsql_ctx *ctx, const gsql_xchg_spec *spec, gsql_xchg **out);

@@ -37,14 +37,15 @@ def test_struct_layouts_match_header_sizes():
     prog = r'''
     #include <stdio.h>
     #include "gsql_gpu.h"
-    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(gsql_col), sizeof(gsql_batch), sizeof(gsql_join_spec),
-                       sizeof(gsql_join_info), sizeof(gsql_agg_call), sizeof(gsql_agg_spec), sizeof(gsql_xchg_spec)); return 0; }
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(gsql_col), sizeof(gsql_batch), sizeof(gsql_join_spec),
+                       sizeof(gsql_join_info), sizeof(gsql_agg_call), sizeof(gsql_agg_spec), sizeof(gsql_xchg_spec),
+                       sizeof(gsql_expr_ins), sizeof(gsql_expr), sizeof(gsql_scan_spec)); return 0; }
     '''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         sizes = list(map(int, subprocess.check_output([os.path.join(d, "t")]).split()))
-    got = [C.sizeof(x) for x in (N.Col, N.Batch, N.JoinSpec, N.JoinInfo, N.AggCall, N.AggSpec, N.XchgSpec)]
+    got = [C.sizeof(x) for x in (N.Col, N.Batch, N.JoinSpec, N.JoinInfo, N.AggCall, N.AggSpec, N.XchgSpec, N.ExprIns, N.Expr, N.ScanSpec)]
     assert got == sizes
 
 
