@@ -256,7 +256,7 @@ void gsql_agg_destroy(gsql_agg *a);
 
 /* ------------------------------------------------------------------------------------------------ filter / project */
 /* Vectorised Filter + Project in one pass (replaces operator/VectorizedFilterExec.java and
- * operator/VectorizedProjectExec.java:40-143 with the expression trees of executor/vectorized/**): rows for which the
+ * operator/VectorizedProjectExec.java:40-143 with the expression trees of the executor.vectorized package): rows for which the
  * filter is TRUE (NULL and FALSE drop, as VectorizedFilterExec keeps only selected positions) are compacted and every
  * output column is an expression over the input columns.  Expressions are postfix programs over a small typed stack:
  * integers are 64-bit two's complement (Java long arithmetic), doubles IEEE; any NULL operand makes arithmetic and

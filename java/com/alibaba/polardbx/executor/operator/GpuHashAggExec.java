@@ -1,14 +1,17 @@
 /*
- * Drop-in for HashAggExec (polardbx-executor/.../operator/HashAggExec.java:37,74-91,133-162) backed by gsql_agg_*.
- * NOT compiled here (no JDK in the build image) — see INTEGRATION.md.
+ * Drop-in for HashAggExec (operator/HashAggExec.java:37,74-91,133-162; AbstractHashAggExec.java:57-63) backed by
+ * gsql_agg_*.  Lives in the operator package because AbstractExecutor's template methods doOpen / doNextChunk / doClose
+ * are package-private (AbstractExecutor.java:87-91).  Compiled where the CN is built (no JDK in this repository's
+ * build image) — see INTEGRATION.md.
  */
-package com.alibaba.polardbx.executor.operator.gpu;
+package com.alibaba.polardbx.executor.operator;
 
-import com.alibaba.polardbx.executor.chunk.Block;
 import com.alibaba.polardbx.executor.chunk.Chunk;
-import com.alibaba.polardbx.executor.operator.AbstractExecutor;
-import com.alibaba.polardbx.executor.operator.ConsumerExecutor;
-import com.alibaba.polardbx.executor.operator.Executor;
+import com.alibaba.polardbx.executor.chunk.GpuChunks;
+import com.alibaba.polardbx.executor.operator.gpu.GpuAggSpec;
+import com.alibaba.polardbx.executor.operator.gpu.GpuDevices;
+import com.alibaba.polardbx.executor.operator.gpu.GpuNative;
+import com.alibaba.polardbx.executor.operator.gpu.GpuTypes;
 import com.alibaba.polardbx.optimizer.context.ExecutionContext;
 import com.alibaba.polardbx.optimizer.core.datatype.DataType;
 import com.google.common.collect.ImmutableList;
@@ -22,8 +25,9 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
 
     private final List<DataType> inputTypes;
     private final List<DataType> outputColumns;
+    private final int[] inputCodes;
     private final int[] groups;
-    private final GpuAggSpec spec; // kinds / columns / filter args derived from List<Aggregator> at plan time
+    private final GpuAggSpec spec; // kinds / columns / filter args derived from the plan's AggregateCalls
     private final int expectedGroups;
 
     private long ctx, agg, in, out;
@@ -33,6 +37,7 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
                           int expectedGroups, ExecutionContext context) {
         super(context);
         this.inputTypes = inputTypes;
+        this.inputCodes = GpuTypes.codes(inputTypes);
         this.groups = groups;
         this.spec = spec;
         this.outputColumns = outputColumns;
@@ -40,17 +45,20 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
     }
 
     @Override
-    public void openConsume() {
+    public synchronized void openConsume() {
+        if (agg != 0) {
+            return; // LocalExchanger.openConsume opens every consumer once, but stay idempotent
+        }
         ctx = GpuNative.ctxCreate(GpuDevices.deviceForThisDriver(context));
-        agg = GpuNative.aggCreate(ctx, GpuTypes.codes(inputTypes), groups, spec.kinds, spec.cols, spec.filterArgs,
-            expectedGroups);
-        in = GpuNative.stagingCreate(GpuTypes.codes(inputTypes), GPU_BATCH_ROWS + chunkLimit);
+        agg = GpuNative.aggCreate(ctx, inputCodes, groups, spec.kinds, spec.cols, spec.filterArgs, expectedGroups);
+        in = GpuNative.stagingCreate(inputCodes, GPU_BATCH_ROWS + chunkLimit);
         out = GpuNative.stagingCreate(GpuTypes.codes(outputColumns), chunkLimit);
     }
 
+    /** Several exchanger threads may feed one consumer (asyncConsume): serialised like ParallelHashJoinExec:158. */
     @Override
-    public void consumeChunk(Chunk chunk) {
-        GpuChunks.append(in, chunk); // Block arrays -> pinned staging (GetPrimitiveArrayCritical inside)
+    public synchronized void consumeChunk(Chunk chunk) {
+        GpuChunks.append(in, chunk, inputCodes); // Block arrays -> pinned staging (GetPrimitiveArrayCritical inside)
         if (GpuNative.stagingRows(in) >= GPU_BATCH_ROWS) {
             GpuNative.aggConsume(agg, in);
             GpuNative.stagingReset(in);
@@ -58,7 +66,7 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
     }
 
     @Override
-    public void buildConsume() {
+    public synchronized void buildConsume() {
         if (GpuNative.stagingRows(in) > 0) {
             GpuNative.aggConsume(agg, in);
             GpuNative.stagingReset(in);
@@ -77,7 +85,10 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
     }
 
     @Override
-    public void closeConsume(boolean force) {
+    public synchronized void closeConsume(boolean force) {
+        if (agg == 0) {
+            return;
+        }
         GpuNative.aggDestroy(agg);
         GpuNative.stagingDestroy(in);
         GpuNative.stagingDestroy(out);
@@ -91,9 +102,7 @@ public class GpuHashAggExec extends AbstractExecutor implements ConsumerExecutor
 
     @Override
     void doClose() {
-        if (agg != 0) {
-            closeConsume(true);
-        }
+        closeConsume(true);
     }
 
     @Override

@@ -1,0 +1,54 @@
+/*
+ * Minimal stand-in for <jni.h>: ONLY what jni/gsql_jni.c uses, with the JNI specification's names and signatures, so
+ * that the shim can be syntax-checked, compiled and linked against libgsql_gpu.so in an image without a JDK
+ * (tests/test_jni_boundary.py).  A real build uses $JAVA_HOME/include/jni.h instead; this file is never shipped.
+ */
+#ifndef GSQL_JNI_STUB_H
+#define GSQL_JNI_STUB_H
+#include <stdint.h>
+
+typedef int32_t jint;
+typedef int64_t jlong;
+typedef uint8_t jboolean;
+typedef double jdouble;
+typedef jint jsize;
+typedef void *jobject;
+typedef jobject jclass;
+typedef jobject jarray;
+typedef jarray jobjectArray;
+typedef jarray jintArray;
+typedef jarray jlongArray;
+typedef jarray jdoubleArray;
+typedef jarray jbooleanArray;
+typedef jobject jthrowable;
+
+#define JNI_ABORT 2
+#define JNI_FALSE 0
+#define JNI_TRUE 1
+#define JNIEXPORT __attribute__((visibility("default")))
+#define JNICALL
+
+struct JNINativeInterface_;
+typedef const struct JNINativeInterface_ *JNIEnv;
+
+struct JNINativeInterface_ {
+    jclass (*FindClass)(JNIEnv *env, const char *name);
+    jint (*ThrowNew)(JNIEnv *env, jclass clazz, const char *msg);
+    jboolean (*ExceptionCheck)(JNIEnv *env);
+    jsize (*GetArrayLength)(JNIEnv *env, jarray array);
+    jobject (*GetObjectArrayElement)(JNIEnv *env, jobjectArray array, jsize index);
+    void (*DeleteLocalRef)(JNIEnv *env, jobject obj);
+    void (*GetIntArrayRegion)(JNIEnv *env, jintArray array, jsize start, jsize len, jint *buf);
+    void (*GetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, jlong *buf);
+    void (*SetIntArrayRegion)(JNIEnv *env, jintArray array, jsize start, jsize len, const jint *buf);
+    void (*SetLongArrayRegion)(JNIEnv *env, jlongArray array, jsize start, jsize len, const jlong *buf);
+    void (*SetDoubleArrayRegion)(JNIEnv *env, jdoubleArray array, jsize start, jsize len, const jdouble *buf);
+    void (*SetBooleanArrayRegion)(JNIEnv *env, jbooleanArray array, jsize start, jsize len, const jboolean *buf);
+    jintArray (*NewIntArray)(JNIEnv *env, jsize len);
+    jlongArray (*NewLongArray)(JNIEnv *env, jsize len);
+    jdoubleArray (*NewDoubleArray)(JNIEnv *env, jsize len);
+    jbooleanArray (*NewBooleanArray)(JNIEnv *env, jsize len);
+    void *(*GetPrimitiveArrayCritical)(JNIEnv *env, jarray array, jboolean *isCopy);
+    void (*ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);
+};
+#endif
