@@ -107,7 +107,7 @@ def section_push(ctx, device, rank, world):
     small = api.Exchange(ctx, [N.T_INT64], [0], world)
     small.open_p2p(1000)
     try:
-        small.push(dev([key], device)[:1], 2)
+        small.push(dev([(key[0], None)], device), 2)
         raise AssertionError("expected a capacity error")
     except N.CapacityError as e:
         assert e.required and e.required > 1000
@@ -145,11 +145,11 @@ def section_agg(ctx, device, rank, world):
     k = ((ku.rand_u64(n, 70 + rank) % np.uint64(25_000)).astype(np.int64), None)
     v = ku.with_nulls((ku.rand_u64(n, 80 + rank) % np.uint64(100_000)).astype(np.float64) / 7.0, 0.03, 90 + rank)
     agg = pipelines.TwoPhaseAgg(ctx, [N.T_INT64, N.T_FP64], [0], [(N.AGG_SUM, [1]), (N.AGG_COUNT, [1]), (N.AGG_COUNT_STAR, []), (N.AGG_AVG, [1])],
-                                expected_groups=25_000, capacity=100_000)
+                                expected_groups=25_000, capacity=400_000, nullable=[1])
     out = host(agg.run(dev([k, v], device)))
     agg.close()
     glob = gather_cols([k, v])
-    exp = orc.hash_agg(glob, [0], [(orc.AGG_SUM, [1]), (orc.AGG_COUNT, [1]), (orc.AGG_COUNT_STAR, []), (orc.AGG_AVG, [1])], 1024)
+    exp = orc.hash_agg(glob, [0], [orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_COUNT, [1]), orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_AVG, [1])], 1024)
     allout = gather_cols(out)
     if rank == 0:
         gu.approx_rows_equal(allout, exp, float_cols=[1, 4], key_cols=[0], rtol=1e-6)

@@ -17,4 +17,7 @@ def test_push_shuffle_join_agg_q3_across_ranks():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", str(29500 + os.getpid() % 2000), os.path.join(ROOT, "tests", "multigpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    if r.returncode != 0:  # keep the whole transcript where a gpurun call brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "multigpu_worker.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
     assert r.returncode == 0 and "MULTIGPU_OK" in r.stdout, (r.stdout[-3000:], r.stderr[-6000:])
