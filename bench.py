@@ -252,6 +252,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     ctx = api.Context(local_rank)
     stream = ctx.torch_stream()
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.tensor(list(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        api.comm_init(ctx, world, rank, bytes(uid.cpu().tolist()))
+    if args.workload != "c2":
+        run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev)
+        if world > 1:
+            ctx.lib.gsql_comm_destroy(ctx.ptr)
+            dist.destroy_process_group()
+        return
 
     nb = int(C2_BUILD * args.scale)
     npr = int(C2_PROBE * args.scale)
@@ -274,11 +286,6 @@ def run_ours(args):
     out_cols = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in out_types]
     if world > 1:
         from galaxysql_b200 import pipelines
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
-        if rank == 0:
-            uid.copy_(torch.tensor(list(api.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        api.comm_init(ctx, world, rank, bytes(uid.cpu().tolist()))
         bcap = int(nb * 1.05) + 1_000_000
         sj = pipelines.ShuffledJoin(ctx, N.JOIN_INNER, types, types, [0], [0], build_capacity=bcap, probe_capacity=cap, nslabs=args.slabs)
 
@@ -395,10 +402,13 @@ def run_ours(args):
     # Never allowed to take the headline down: any failure is reported inside the key.
     aux = None
     if rank == 0 and world == 1 and not args.no_aux:
-        try:
-            aux = {"agg_q1_shape": run_aux_agg(ctx, api, N, synth, dev, args.scale, peak)}
-        except Exception as e:  # noqa: BLE001
-            aux = {"agg_q1_shape": {"error": f"{type(e).__name__}: {e}"[:300]}}
+        del out_cols, probe, build    # ~50 GB back before the aggregation tables are generated
+        torch.cuda.empty_cache()
+        for key, fn in (("agg_q1", run_aux_agg), ("agg_c5", run_aux_agg_c5), ("agg_c1", run_aux_agg_c1)):
+            try:
+                roofline[key] = fn(ctx, api, N, synth, dev, args.scale, peak)
+            except Exception as e:  # noqa: BLE001
+                roofline[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         info = state["info"]
         line = {
@@ -415,8 +425,6 @@ def run_ours(args):
             "clocks": clocks,
             "gpu_launches": int(launches),
         }
-        if aux:
-            line["aux"] = aux
         if e2e:
             line["e2e"] = e2e
         if cpu:
@@ -471,10 +479,40 @@ def verify_join_checksum(torch, dist, synth, dev, world, rank, nb, npr, probe, o
             "what": "sum over all output rows of mix64(probe.key,p1,p2,b1,b2), all ranks, vs the same sum derived from the inputs"}
 
 
+def _timed_agg(ctx, make, feed, reps=3):
+    """Best wall time of consume+finish over `reps` fresh handles (after one warm-up), and the kernel times of that run."""
+    import time as _t
+    best, groups, prof_best = None, 0, {}
+    for i in range(reps + 1):
+        a = make()
+        ctx.sync()
+        ctx.profile(True)
+        ctx.profile_reset()
+        t0 = _t.perf_counter()
+        feed(a)
+        groups = a.finish()
+        ctx.sync()
+        dt = _t.perf_counter() - t0
+        prof = ctx.profile_dump()
+        ctx.profile(False)
+        a.close()
+        if i > 0 and (best is None or dt < best):
+            best, prof_best = dt, prof
+    return best, groups, prof_best
+
+
+def _agg_entry(rows, groups, alg_bytes, best_s, prof, peak_gbs, what):
+    kern_ms = sum(v[1] for k, v in prof.items() if k.startswith("agg_") and k not in ("agg_slots_init", "agg_state_init", "agg_finalize"))
+    top = max(((v[1], k) for k, v in prof.items() if k.startswith("agg_")), default=(0.0, ""))[1]
+    gbs = rows * alg_bytes / (kern_ms / 1e3) / 1e9 if kern_ms > 0 else 0.0
+    return {"workload": what, "rows": rows, "groups": int(groups), "algorithmic_bytes_per_row": alg_bytes, "ms_wall": best_s * 1e3,
+            "rows_per_s": rows / best_s, "kernel_ms": kern_ms, "achieved": gbs, "peak": peak_gbs, "unit": "GB/s", "frac": gbs / peak_gbs,
+            "kernel": top, "per_kernel_ms": {k: v[1] for k, v in sorted(prof.items())}}
+
+
 def run_aux_agg(ctx, api, N, synth, dev, scale, peak_gbs):
     """BASELINE config 3 shape (TPC-H Q1): 600 M rows, 2 INT keys (3 x 2 values), 8 aggregates over DOUBLE columns,
-    44 algorithmic bytes per row; one gsql_agg_consume + gsql_agg_finish over device-resident columns,
-    best of 2 after a warm-up, wall clock around the synchronous calls (same procedure as tools/aggbench.py)."""
+    44 algorithmic bytes per row; one gsql_agg_consume + gsql_agg_finish over device-resident columns."""
     import torch
     n3 = int(600_037_902 * scale)
     flag = synth.rand_i64_t(n3, 4, dev, post=lambda b: synth._u64_mod(b, 3).to(torch.int32))
@@ -486,24 +524,185 @@ def run_aux_agg(ctx, api, N, synth, dev, scale, peak_gbs):
     ship = synth.rand_i64_t(n3, 10, dev, post=lambda b: (synth._u64_mod(b, 2526) + 8036).to(torch.int32))
     cols = [flag, status, qty, price, disc, tax, ship]
     types = [0, 0, 2, 2, 2, 2, 0]
-    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [4]), (N.AGG_SUM, [5]), (N.AGG_AVG, [2]), (N.AGG_AVG, [3]),
+    # the Q1 plan: SUM(qty), SUM(price), SUM(price*(1-disc)), SUM(price*(1-disc)*(1+tax)), AVG(qty), AVG(price), AVG(disc), COUNT(*),
+    # l_shipdate <= 1998-09-02 — Project and Filter fused into the aggregation (gsql_agg_spec.derived / row_filter_*)
+    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [7]), (N.AGG_SUM, [8]), (N.AGG_AVG, [2]), (N.AGG_AVG, [3]),
             (N.AGG_AVG, [4]), (N.AGG_COUNT_STAR, [])]
+    derived = [(N.EXPR_MUL_1MINUS, 3, 4, 0), (N.EXPR_MUL_1MINUS_1PLUS, 3, 4, 5)]
     torch.cuda.synchronize()
-    best, groups = None, 0
-    for i in range(3):
-        a = api.HashAgg(ctx, types, [0, 1], aggs, 8)
-        ctx.sync()
-        t0 = time.perf_counter()
-        a.consume([(c, None) for c in cols])
-        groups = a.finish()
-        ctx.sync()
-        dt = time.perf_counter() - t0
-        a.close()
-        if i > 0 and (best is None or dt < best):
-            best = dt
-    gbs = n3 * 44 / best / 1e9
-    return {"rows": n3, "groups": int(groups), "ms": best * 1e3, "rows_per_s": n3 / best, "algorithmic_bytes_per_row": 44,
-            "achieved_gbs": gbs, "frac_of_peak": gbs / peak_gbs, "kernel": "k_agg_lane (lane-private shared-memory accumulators)"}
+    best, groups, prof = _timed_agg(ctx, lambda: api.HashAgg(ctx, types, [0, 1], aggs, 8, derived=derived, row_filter=(6, N.CMP_LE, 10471)),
+                                    lambda a: a.consume([(c, None) for c in cols]))
+    return _agg_entry(n3, groups, 44, best, prof, peak_gbs, "C3: TPC-H Q1 shape, 600M rows, fused project + filter, 8 aggregates")
+
+
+def run_aux_agg_c5(ctx, api, N, synth, dev, scale, peak_gbs):
+    """One GPU's share of BASELINE config 5 after the shuffle: 500 M rows, 6.25 M distinct BIGINT keys, SUM(double);
+    16 algorithmic bytes per row."""
+    import torch
+    n = int(500_000_000 * scale)
+    keys = int(6_250_000 * scale) or 1
+    k = synth.rand_i64_t(n, 11, dev, post=lambda b: synth._u64_mod(b, keys) * 8 + 3)
+    v = synth.rand_i64_t(n, 12, dev, post=lambda b: synth._lsr(b, 11).to(torch.float64) / float(1 << 53))
+    torch.cuda.synchronize()
+    best, groups, prof = _timed_agg(ctx, lambda: api.HashAgg(ctx, [N.T_INT64, N.T_FP64], [0], [(N.AGG_SUM, [1])], keys),
+                                    lambda a: a.consume([(k, None), (v, None)]))
+    return _agg_entry(n, groups, 16, best, prof, peak_gbs, "C5 share: 500M rows, 6.25M distinct keys, SUM(double)")
+
+
+def run_aux_agg_c1(ctx, api, N, synth, dev, scale, peak_gbs):
+    """BASELINE config 1: SELECT k, COUNT(*) FROM t GROUP BY k, 1 M-row INT column, k in [0, 65536); 4 bytes per row."""
+    import torch
+    n = 1_000_000
+    k = synth.rand_i64_t(n, 13, dev, post=lambda b: synth._u64_mod(b, 65536).to(torch.int32))
+    torch.cuda.synchronize()
+    best, groups, prof = _timed_agg(ctx, lambda: api.HashAgg(ctx, [N.T_INT32], [0], [(N.AGG_COUNT_STAR, [])], 65535),
+                                    lambda a: a.consume([(k, None)]), reps=5)
+    return _agg_entry(n, groups, 4, best, prof, peak_gbs, "C1: 1M-row INT column, COUNT(*) (launch-bound)")
+
+
+# ------------------------------------------------------------------------------------------------ q3 / c5 pipelines
+def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
+    """--workload q3: BASELINE config 4 (TPC-H Q3, SF300 over 8 GPUs = SF37.5 per GPU, weak scaling);
+    --workload c5: BASELINE config 5 (GROUP BY k, SUM(double): 500 M rows and 6.25 M keys per GPU).  One step = the whole
+    pipeline of galaxysql_b200/pipelines.py over device-resident tables; value = input rows of all ranks / max step time."""
+    import torch
+    import torch.distributed as dist
+    from galaxysql_b200 import api, native as N, pipelines, synth
+    sc = args.scale
+    peak, peak_src = measured_peak_gbs()
+    if args.workload == "q3":
+        ncust, nord, nline = int(5_625_000 * sc), int(56_250_000 * sc), int(225_000_000 * sc)
+        g = torch.Generator(device=dev)
+        g.manual_seed(1000 + rank)
+        c_custkey = torch.arange(ncust, dtype=torch.int64, device=dev) * world + rank
+        c_seg = synth.rand_i64_t(ncust, 20, dev, start=rank * ncust, post=lambda b: synth._u64_mod(b, 5).to(torch.int32))
+        o_orderkey = torch.randperm(nord, generator=g, device=dev, dtype=torch.int64) * world + rank
+        o_custkey = synth.rand_i64_t(nord, 21, dev, start=rank * nord, post=lambda b: synth._u64_mod(b, ncust * world))
+        o_date = synth.rand_i64_t(nord, 22, dev, start=rank * nord, post=lambda b: (synth._u64_mod(b, 2557) + 8035).to(torch.int32))
+        o_ship = torch.zeros(nord, dtype=torch.int32, device=dev)
+        l_orderkey = synth.rand_i64_t(nline, 23, dev, start=rank * nline, post=lambda b: synth._u64_mod(b, nord * world))
+        l_price = synth.rand_i64_t(nline, 24, dev, start=rank * nline, post=lambda b: (synth._u64_mod(b, 10_410_000) + 90_000).to(torch.float64) / 100.0)
+        l_disc = synth.rand_i64_t(nline, 25, dev, start=rank * nline, post=lambda b: synth._u64_mod(b, 11).to(torch.float64) / 100.0)
+        l_shipd = synth.rand_i64_t(nline, 26, dev, start=rank * nline, post=lambda b: (synth._u64_mod(b, 2557) + 8035).to(torch.int32))
+        cust = [(c_custkey, None), (c_seg, None)]
+        orders = [(o_orderkey, None), (o_custkey, None), (o_date, None), (o_ship, None)]
+        line = [(l_orderkey, None), (l_price, None), (l_disc, None), (l_shipd, None)]
+        q3 = pipelines.Q3Pipeline(ctx, customer_capacity=int(ncust * world * 0.25) + 100_000, orders_capacity=int(nord * 0.2) + 100_000,
+                                  lineitem_capacity=int(nline * 0.75) + 1_000_000, nslabs=args.slabs, expected_groups=int(nord * 0.1) + 1024)
+        state = {}
+
+        def step():
+            state["out"] = q3.run(cust, orders, line)
+
+        rows_in = ncust + nord + nline
+        what = f"C4: TPC-H Q3 (3-way hash join + group-by), SF{300 * sc / 8:.1f} per GPU x {world} GPUs; customer {ncust} / orders {nord} / lineitem {nline} rows per GPU"
+    else:
+        n = int(500_000_000 * sc)
+        keys = max(int(6_250_000 * sc) * world, 1)
+        k = synth.rand_i64_t(n, 30, dev, start=rank * n, post=lambda b: synth._u64_mod(b, keys) * 8 + 3)
+        v = synth.rand_i64_t(n, 31, dev, start=rank * n, post=lambda b: synth._lsr(b, 11).to(torch.float64) / float(1 << 53))
+        agg = pipelines.TwoPhaseAgg(ctx, [N.T_INT64, N.T_FP64], [0], [(N.AGG_SUM, [1]), (N.AGG_COUNT_STAR, [])], expected_groups=keys,
+                                    capacity=int(n * 1.03) + 1_000_000, nslabs=args.slabs, expected_rows=n * world)
+        state = {}
+
+        def step():
+            state["out"] = agg.run([(k, None), (v, None)])
+
+        rows_in = n
+        what = f"C5: GROUP BY k, SUM(double): {n} rows per GPU x {world} GPUs, {keys} distinct keys ({agg.mode} plan)"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ctx.profile(True)
+    ctx.profile_reset()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms_total = ev0.elapsed_time(ev1)
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    # ---- parity of the last step's result against a torch restatement of the query on the same tables (outside the timed region)
+    out = state["out"]
+    if args.workload == "q3":
+        def allgather(t):
+            if world == 1:
+                return t
+            n_ = torch.tensor([t.numel()], dtype=torch.int64, device=dev)
+            ns = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+            dist.all_gather(ns, n_)
+            m = int(max(int(x.item()) for x in ns))
+            pad = torch.zeros(m, dtype=t.dtype, device=dev)
+            pad[:t.numel()] = t
+            outs = [torch.zeros(m, dtype=t.dtype, device=dev) for _ in range(world)]
+            dist.all_gather(outs, pad)
+            return torch.cat([o[:int(x.item())] for o, x in zip(outs, ns)])
+        building = allgather(c_custkey[c_seg == pipelines.Q3_SEGMENT])
+        omask = (o_date < pipelines.Q3_DATE) & torch.isin(o_custkey, building)
+        qual = allgather(o_orderkey[omask])
+        lmask = (l_shipd > pipelines.Q3_DATE)
+        lk = l_orderkey[lmask]
+        hit = torch.isin(lk, qual)
+        exp_rev = (l_price[lmask][hit] * (1.0 - l_disc[lmask][hit])).sum()
+        exp_rows = hit.sum()
+        got = torch.stack([out[3][0].sum(), torch.tensor(float(out[0][0].numel()), dtype=torch.float64, device=dev)])
+        exp = torch.stack([exp_rev, exp_rows.to(torch.float64)])
+        joined_keys = allgather(lk[hit])   # collective: every rank takes part, rank 0 counts the distinct order keys
+        exp_groups = torch.tensor([torch.unique(joined_keys).numel() if rank == 0 else 0], dtype=torch.float64, device=dev)
+        del joined_keys
+        if world > 1:
+            dist.all_reduce(got)
+            dist.all_reduce(exp)
+            dist.all_reduce(exp_groups)
+        rel = abs(float(got[0]) - float(exp[0])) / max(abs(float(exp[0])), 1e-300)
+        parity = {"match": bool(rel < 1e-9 and int(got[1]) == int(exp_groups[0])), "revenue_rel_err": rel, "groups": int(got[1]),
+                  "expected_groups": int(exp_groups[0]), "joined_lineitem_rows": int(exp[1]),
+                  "what": "sum of revenue over all groups and number of groups vs a torch restatement (isin / unique) of Q3 on the same tables"}
+        stats = q3.stats
+    else:
+        got = torch.stack([out[1][0].sum(), out[2][0].sum().to(torch.float64), torch.tensor(float(out[0][0].numel()), dtype=torch.float64, device=dev)])
+        exp = torch.stack([v.sum(), torch.tensor(float(n), dtype=torch.float64, device=dev)])
+        if world > 1:
+            dist.all_reduce(got)
+            dist.all_reduce(exp)
+        rel = abs(float(got[0]) - float(exp[0])) / max(abs(float(exp[0])), 1e-300)
+        parity = {"match": bool(rel < 1e-9 and int(got[1]) == int(exp[1]) and int(got[2]) <= keys), "sum_rel_err": rel, "count": int(got[1]),
+                  "groups": int(got[2]), "what": "sum of SUM(v) and of COUNT(*) over all groups vs the column totals; groups <= distinct keys"}
+        stats = {"mode": agg.mode}
+    assert parity["match"], parity
+    if rank == 0:
+        value = rows_in * world / (ms_step / 1e3)
+        alg = None
+        line_ = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                 "dtype": "f64" if args.workload == "c5" else "int64+f64", "data": "synthetic",
+                 "config": {"workload": what, "slabs": args.slabs, "scale": sc, "l2": "tables are far larger than the 126 MB L2; no explicit flush"},
+                 "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                              "per_kernel_ms_per_step": {k_: v_[1] / args.steps for k_, v_ in sorted(prof.items())}, "peak_source": peak_src},
+                 "parity": parity, "stats": stats, "clocks": clocks, "gpu_launches": int(launches)}
+        print(json.dumps(line_), flush=True)
 
 
 def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):

@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ Agg
     }
 }
 
-// ---- optional pre-pass for tables beyond L2 (GSQL_AGG_PARTITION=1; parity-checked on B200, not measured yet, hence not the default): the batch is reordered by
+// ---- pre-pass for tables beyond L2 (default; GSQL_AGG_PARTITION=0 disables): the batch is reordered by
 // the high bits of the same hash that picks the table slot, so that k_agg_consume — which walks rows in index order —
 // touches one L2-sized slice of the slot array at a time; dense group ids are handed out in first-appearance order,
 // so the accumulators of a slice's groups are contiguous (and L2-resident) as well.  Same idea as the radix mode of
@@ -488,6 +488,7 @@ int agg_out_type(int kind, int in_type) {
 
 #include "agg_fast.cuh"
 #include "agg_lane.cuh"
+#include "agg_reg.cuh"
 
 struct gsql_agg {
     gsql_ctx *ctx;
@@ -509,6 +510,7 @@ struct gsql_agg {
     int64_t cursor = 0;
     AggFast fast;
     AggLane lane;
+    AggReg reg;
     int64_t fallback_total = 0;  // counters[C_FALLBACK] as of the last read (cumulative on the device)
 };
 
@@ -660,10 +662,12 @@ extern "C" gsql_status gsql_agg_create(gsql_ctx *ctx, const gsql_agg_spec *spec,
     agg_fast_plan(&a->fast, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     if (s.expected_groups > (1 << 16)) a->fast.enabled = false;  // the planner expects far more groups than warp tables hold
     agg_lane_check(&a->lane, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
+    agg_reg_check(&a->reg, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type);
     for (int i = 0; i < s.naggs; i++)
         if (s.aggs[i].kind == GSQL_AGG_AVG_MERGE) {  // the privatised kernels do not know the two-column merge
             a->fast.eligible = a->fast.enabled = false;
             a->lane.shape_ok = a->lane.enabled = false;
+            a->reg.shape_ok = a->reg.enabled = false;
         }
     if (getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) a->fast.eligible = a->fast.enabled = false;
     if ((getenv("GSQL_AGG_NO_FAST") && atoi(getenv("GSQL_AGG_NO_FAST"))) || (getenv("GSQL_AGG_NO_LANE") && atoi(getenv("GSQL_AGG_NO_LANE"))))
@@ -776,12 +780,12 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
     StagedBatch sb;
     GSQL_TRY(stage_batch(ctx, batch, &sb));
     GSQL_TRY(a->overflow.grow(ctx, (size_t)batch->rows * 8, 0));
-    // opt-in (GSQL_AGG_PARTITION=1): a large batch headed for the generic kernel against a table beyond L2 is first
-    // reordered by table-slot range
+    // a large batch headed for the generic kernel against a table beyond L2 is first reordered by table-slot range
+    // (GSQL_AGG_PARTITION=0 switches the pre-pass off)
     DevBuf part_data[GSQL_MAX_COLS], part_nulls[GSQL_MAX_COLS];
     {
-        const bool part_on = getenv("GSQL_AGG_PARTITION") && atoi(getenv("GSQL_AGG_PARTITION"));
-        const bool generic = !(a->lane.shape_ok && a->lane.enabled) && !(a->fast.eligible && a->fast.enabled);
+        const bool part_on = getenv("GSQL_AGG_PARTITION") ? atoi(getenv("GSQL_AGG_PARTITION")) != 0 : true;  // default on (r02)
+        const bool generic = !(a->lane.shape_ok && a->lane.enabled) && !(a->fast.eligible && a->fast.enabled) && !(a->reg.shape_ok && a->reg.enabled);
         int64_t per_group = 2 * (int64_t)sizeof(ASlot) + (int64_t)a->nkeys * 9 + (int64_t)a->naggs * 9;
         int64_t table_bytes = (a->gcap + a->slack) * per_group;
         int64_t min_rows = getenv("GSQL_AGG_PARTITION_MIN_ROWS") ? atoll(getenv("GSQL_AGG_PARTITION_MIN_ROWS")) : (1ll << 22);
@@ -803,10 +807,25 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         // three kernels, most specialised first: lane-private accumulators (a handful of groups), warp-private
         // shared-memory tables (tens of groups), the generic global table; the first two are adaptive
         LanePlan LP;
-        const bool use_lane = first && a->lane.shape_ok && a->lane.enabled &&
+        RegPlan RP;
+        const bool use_reg = first && a->reg.shape_ok && a->reg.enabled && agg_reg_plan(&RP, a->spec, a->nkeys, a->naggs, a->spec.aggs, P.in);
+        const bool use_lane = !use_reg && first && a->lane.shape_ok && a->lane.enabled &&
                               agg_lane_plan(&LP, a->spec, a->nkeys, a->naggs, a->spec.aggs, a->in_type, P.in);
-        const bool use_smem = !use_lane && first && a->fast.eligible && a->fast.enabled;
-        if (use_lane) {
+        const bool use_smem = !use_reg && !use_lane && first && a->fast.eligible && a->fast.enabled;
+        if (use_reg) {  // register accumulators: NULL-free batch, <= 8 groups, fp64 sums (the Q1 shape)
+            KernelScope ks(ctx, "agg_reg");
+            int64_t tiles = div_up(P.rows, RG_THREADS * RG_RPT);
+            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, tiles);
+            if (grid < 1) grid = 1;
+            switch (RP.nsrc) {
+            case 1: k_agg_reg<1, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            case 2: k_agg_reg<2, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            case 3: k_agg_reg<3, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            case 4: k_agg_reg<4, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            case 5: k_agg_reg<5, 6><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            default: k_agg_reg<6, 6><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            }
+        } else if (use_lane) {
             KernelScope ks(ctx, "agg_lane");
             int64_t steps = div_up(P.rows, 32 * LA_R * LA_WARPS);
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count, steps);
@@ -836,7 +855,11 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         {  // adaptive: stop using a privatised kernel when its small tables do not hold the key set
             const int64_t fell = (int64_t)h[C_FALLBACK] - a->fallback_total;
             a->fallback_total = (int64_t)h[C_FALLBACK];
-            if (use_lane) {
+            if (use_reg) {
+                a->reg.rows_seen += P.rows;
+                a->reg.rows_fallback += fell;
+                if (a->reg.rows_seen >= (1 << 16) && a->reg.rows_fallback * 8 > a->reg.rows_seen) a->reg.enabled = false;
+            } else if (use_lane) {
                 a->lane.rows_seen += P.rows;
                 a->lane.rows_fallback += fell;
                 if (a->lane.rows_seen >= (1 << 16) && a->lane.rows_fallback * 8 > a->lane.rows_seen) a->lane.enabled = false;
@@ -854,7 +877,7 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         }
         // the privatised kernels merge warp-private groups past gcap (into the slack): beyond a few tens of thousands of
         // groups they cannot win any more, and every launch may add warps x S groups unchecked
-        if (a->ngroups > (1 << 16)) a->lane.enabled = a->fast.enabled = false;
+        if (a->ngroups > (1 << 16)) a->lane.enabled = a->fast.enabled = a->reg.enabled = false;
         int64_t nover = (int64_t)h[C_OVERFLOW];
         if (nover == 0) {
             // merges that ignored the cap may have eaten into the slack: restore it before the next launch

@@ -74,7 +74,8 @@ struct KernelScope {
     gsql_ctx *ctx;
     int idx = -1;
     cudaEvent_t start = nullptr;
-    KernelScope(gsql_ctx *c, const char *name);
+    cudaStream_t stream = nullptr;  // the stream the kernel is launched on (default: the context stream)
+    KernelScope(gsql_ctx *c, const char *name, cudaStream_t on = nullptr);
     ~KernelScope();
 };
 

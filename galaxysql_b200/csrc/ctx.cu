@@ -124,7 +124,7 @@ static cudaEvent_t take_event(gsql_ctx *ctx) {
     return e;
 }
 
-KernelScope::KernelScope(gsql_ctx *c, const char *name) : ctx(c) {
+KernelScope::KernelScope(gsql_ctx *c, const char *name, cudaStream_t on) : ctx(c), stream(on ? on : c->stream) {
     c->launches++;
     if (!c->profiling) return;
     for (size_t i = 0; i < c->prof.size(); i++)
@@ -135,13 +135,13 @@ KernelScope::KernelScope(gsql_ctx *c, const char *name) : ctx(c) {
         idx = (int)c->prof.size() - 1;
     }
     start = take_event(c);
-    cudaEventRecord(start, c->stream);
+    cudaEventRecord(start, stream);
 }
 
 KernelScope::~KernelScope() {
     if (idx < 0) return;
     cudaEvent_t stop = take_event(ctx);
-    cudaEventRecord(stop, ctx->stream);
+    cudaEventRecord(stop, stream);
     ctx->prof[idx].pending.emplace_back(start, stop);
     ctx->prof[idx].launches++;
 }
@@ -151,6 +151,7 @@ static void prof_resolve(gsql_ctx *ctx) {
     for (auto &p : ctx->prof) {
         for (auto &ev : p.pending) {
             float ms = 0;
+            cudaEventSynchronize(ev.second);  // kernels of an exchange run on its own stream
             if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) p.ms += ms;
             ctx->event_pool.push_back(ev.first);
             ctx->event_pool.push_back(ev.second);

@@ -610,6 +610,60 @@ struct PushParams {
     int64_t null_off[GSQL_MAX_COLS];        // byte offset of column c's NULL bytes, or -1
 };
 
+// Destination of row r.  FAST: one integer key column without a NULL buffer, hash mode — the shape of every join / group
+// key exchange in the benchmarks; everything else goes through the generic row hash.
+template <bool FAST>
+__device__ __forceinline__ int push_dest(const XParams &P, int64_t r) {
+    if (FAST) {
+        const DCol &c = P.keys.c[0];
+        int32_t h;
+        if (c.type == GSQL_T_INT32) {
+            const int v = ld_stream_4(reinterpret_cast<const int *>(c.data) + r);
+            h = P.keys.utype[0] == GSQL_T_INT32 ? v : gsql_hash_i64((int64_t)v);
+        } else {
+            h = gsql_hash_i64(ld_stream_8(reinterpret_cast<const long long *>(c.data) + r));
+        }
+        return gsql_partition_of(h, P.nparts, P.pow2 != 0);
+    }
+    return row_part(P, r);
+}
+
+static bool push_fast_key(const XParams &X) {
+    return X.mode == GSQL_XCHG_HASH && X.keys.n == 1 && X.keys.c[0].nulls == nullptr && X.keys.c[0].type != GSQL_T_FP64 &&
+           X.keys.utype[0] != GSQL_T_FP64 && !(X.keys.c[0].type == GSQL_T_INT64 && X.keys.utype[0] == GSQL_T_INT32);
+}
+
+// hist[dst * nblocks + b] = rows of block b's chunk routed to dst.  Same block geometry as k_xchg_push.  Four rows per
+// thread are in flight; a warp adds one shared-memory count per distinct destination (match.any), not one per row.
+template <bool FAST>
+__global__ void __launch_bounds__(PUSH_THREADS) k_push_hist(const __grid_constant__ XParams P, int64_t *__restrict__ hist) {
+    __shared__ unsigned int sh[GSQL_MAX_RANKS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid < GSQL_MAX_RANKS) sh[tid] = 0;
+    __syncthreads();
+    const int64_t r0 = (int64_t)blockIdx.x * P.chunk;
+    const int64_t r1 = r0 + P.chunk < P.rows ? r0 + P.chunk : P.rows;
+    for (int64_t t0 = r0; t0 < r1; t0 += PUSH_TILE) {
+        int d[PUSH_RPT];
+#pragma unroll
+        for (int k = 0; k < PUSH_RPT; k++) {
+            const int64_t r = t0 + k * PUSH_THREADS + tid;
+            d[k] = r < r1 ? push_dest<FAST>(P, r) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < PUSH_RPT; k++) {
+            const unsigned peers = __match_any_sync(0xffffffffu, d[k]);
+            if (d[k] >= 0 && (peers & ((1u << lane) - 1u)) == 0) atomicAdd(&sh[d[k]], (unsigned)__popc(peers));
+        }
+    }
+    __syncthreads();
+    if (tid < P.nparts) hist[(int64_t)tid * P.nblocks + blockIdx.x] = sh[tid];
+}
+
+// NC > 0: the NC columns of the batch (no NULL buffers) are loaded into registers together with the keys, before the
+// ranking: every global load of a tile is in flight at once.  NC = 0: generic (any column count, NULL masks), one column
+// at a time.
+template <bool FAST, int NC>
 __global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_constant__ PushParams P) {
     __shared__ __align__(16) unsigned long long stage[2][PUSH_TILE];  // one column of the tile in destination order (double-buffered)
     __shared__ unsigned char sdest[PUSH_TILE];                        // destination of each staged position
@@ -628,15 +682,29 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_cons
     for (int64_t t0 = r0; t0 < r1; t0 += PUSH_TILE) {
         const int n_tile = (int)(r1 - t0 < PUSH_TILE ? r1 - t0 : PUSH_TILE);
         for (int i = tid; i < R * PUSH_CELLS; i += PUSH_THREADS) cell[i] = 0;
-        __syncthreads();  // also orders the previous tile's last flush / cur update before this tile's writes
-        // 1. destination of this thread's rows and their rank among the warp's rows with the same destination
+        // 1. destination of this thread's rows (+ all their column values when NC > 0)
         int d[PUSH_RPT];
         unsigned int rank[PUSH_RPT];
+        unsigned long long pre[NC > 0 ? NC : 1][PUSH_RPT];
 #pragma unroll
         for (int k = 0; k < PUSH_RPT; k++) {
             const int64_t r = t0 + k * PUSH_THREADS + tid;
-            d[k] = r < r1 ? row_part(P.X, r) : -1;
+            d[k] = r < r1 ? push_dest<FAST>(P.X, r) : -1;
         }
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const DCol &col = P.X.in.c[c];
+            const bool is32 = col.type == GSQL_T_INT32;
+#pragma unroll
+            for (int k = 0; k < PUSH_RPT; k++) {
+                const int64_t r = t0 + k * PUSH_THREADS + tid;
+                pre[c][k] = 0;
+                if (r < r1) pre[c][k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
+                                             : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+            }
+        }
+        __syncthreads();  // cells are zero; also orders the previous tile's last flush / cur update before this tile's writes
+        // 2. rank among the warp's rows with the same destination; per (dst, warp, slot) counts
 #pragma unroll
         for (int k = 0; k < PUSH_RPT; k++) {
             const unsigned peers = __match_any_sync(0xffffffffu, d[k]);
@@ -644,7 +712,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_cons
             if (d[k] >= 0 && rank[k] == 0) cell[d[k] * PUSH_CELLS + warp * PUSH_RPT + k] = __popc(peers);
         }
         __syncthreads();
-        {  // 2. exclusive scan of the cells in (dst, warp, slot) order: a destination's rows become one run of the tile
+        {  // exclusive scan of the cells in (dst, warp, slot) order: a destination's rows become one run of the tile
             unsigned int v[IPT];
 #pragma unroll
             for (int i = 0; i < IPT; i++) {
@@ -675,53 +743,61 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) k_xchg_push(const __grid_cons
         // 3. column after column: stage in destination order, then consecutive threads store consecutive elements of a
         //    destination's run into that GPU's receive buffer
         int phase = 0;
-#pragma unroll 1
-        for (int c = 0; c < P.X.in.n; c++) {
-            const DCol &col = P.X.in.c[c];
-            const bool is32 = col.type == GSQL_T_INT32;
-            unsigned long long v[PUSH_RPT];
-#pragma unroll
-            for (int k = 0; k < PUSH_RPT; k++) {
-                const int64_t r = t0 + k * PUSH_THREADS + tid;
-                v[k] = 0;
-                if (d[k] >= 0) v[k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
-                                           : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
-            }
-            unsigned long long *st = stage[phase];
-#pragma unroll
-            for (int k = 0; k < PUSH_RPT; k++)
-                if (d[k] >= 0) st[pos[k]] = v[k];
-            __syncthreads();
+        auto flush = [&](int c, bool is32, const unsigned long long *st, bool nulls) {
 #pragma unroll
             for (int k = 0; k < PUSH_RPT; k++) {
                 const int i = k * PUSH_THREADS + tid;
                 if (i < n_tile) {
                     const int dd = sdest[i];
                     const unsigned long long row = cur[dd] + (unsigned)(i - (int)dstart[dd]);
-                    char *dst = P.peer_base[dd] + P.col_off[c];
-                    if (is32) reinterpret_cast<int *>(dst)[row] = (int)(unsigned)st[i];
-                    else reinterpret_cast<long long *>(dst)[row] = (long long)st[i];
+                    if (nulls) reinterpret_cast<uint8_t *>(P.peer_base[dd] + P.null_off[c])[row] = (uint8_t)st[i];
+                    else if (is32) reinterpret_cast<int *>(P.peer_base[dd] + P.col_off[c])[row] = (int)(unsigned)st[i];
+                    else reinterpret_cast<long long *>(P.peer_base[dd] + P.col_off[c])[row] = (long long)st[i];
                 }
             }
-            phase ^= 1;
-            if (P.null_off[c] >= 0) {  // NULL bytes travel the same way
-                unsigned long long *sn = stage[phase];
+        };
+        if (NC > 0) {
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                unsigned long long *st = stage[phase];
+#pragma unroll
+                for (int k = 0; k < PUSH_RPT; k++)
+                    if (d[k] >= 0) st[pos[k]] = pre[c][k];
+                __syncthreads();
+                flush(c, P.X.in.c[c].type == GSQL_T_INT32, st, false);
+                phase ^= 1;
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < P.X.in.n; c++) {
+                const DCol &col = P.X.in.c[c];
+                const bool is32 = col.type == GSQL_T_INT32;
+                unsigned long long v[PUSH_RPT];
 #pragma unroll
                 for (int k = 0; k < PUSH_RPT; k++) {
                     const int64_t r = t0 + k * PUSH_THREADS + tid;
-                    if (d[k] >= 0) sn[pos[k]] = col.nulls ? (unsigned long long)col.nulls[r] : 0ULL;
+                    v[k] = 0;
+                    if (d[k] >= 0) v[k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
+                                               : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
                 }
-                __syncthreads();
+                unsigned long long *st = stage[phase];
 #pragma unroll
-                for (int k = 0; k < PUSH_RPT; k++) {
-                    const int i = k * PUSH_THREADS + tid;
-                    if (i < n_tile) {
-                        const int dd = sdest[i];
-                        const unsigned long long row = cur[dd] + (unsigned)(i - (int)dstart[dd]);
-                        reinterpret_cast<uint8_t *>(P.peer_base[dd] + P.null_off[c])[row] = (uint8_t)sn[i];
-                    }
-                }
+                for (int k = 0; k < PUSH_RPT; k++)
+                    if (d[k] >= 0) st[pos[k]] = v[k];
+                __syncthreads();
+                flush(c, is32, st, false);
                 phase ^= 1;
+                if (P.null_off[c] >= 0) {  // NULL bytes travel the same way
+                    unsigned long long *sn = stage[phase];
+#pragma unroll
+                    for (int k = 0; k < PUSH_RPT; k++) {
+                        const int64_t r = t0 + k * PUSH_THREADS + tid;
+                        if (d[k] >= 0) sn[pos[k]] = col.nulls ? (unsigned long long)col.nulls[r] : 0ULL;
+                    }
+                    __syncthreads();
+                    flush(c, false, sn, true);
+                    phase ^= 1;
+                }
             }
         }
         __syncthreads();
@@ -956,8 +1032,9 @@ extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_
         }
         GSQL_CUDA(ctx, cudaMemsetAsync(x->hist[i].p, 0, (size_t)(nh + 1) * 8, ps));
         if (X.rows > 0) {
-            ctx->launches++;
-            k_xchg_hist<<<X.nblocks, XBLOCK, (size_t)R * sizeof(unsigned int), ps>>>(X, x->hist[i].as<int64_t>());
+            KernelScope ks(ctx, "xchg_push_hist", ps);
+            if (push_fast_key(X)) k_push_hist<true><<<X.nblocks, PUSH_THREADS, 0, ps>>>(X, x->hist[i].as<int64_t>());
+            else k_push_hist<false><<<X.nblocks, PUSH_THREADS, 0, ps>>>(X, x->hist[i].as<int64_t>());
         }
         size_t tb = x->scan_tmp.bytes;
         GSQL_CUDA(ctx, cub::DeviceScan::ExclusiveSum(x->scan_tmp.p, tb, x->hist[i].as<int64_t>(), x->offs[i].as<int64_t>(), nh + 1, ps));
@@ -1014,13 +1091,37 @@ extern "C" gsql_status gsql_xchg_push(gsql_xchg *x, const gsql_batch *in, int32_
                 PP.col_off[c] = x->col_off[c];
                 PP.null_off[c] = x->null_off[c];
             }
-            ctx->launches++;
-            if (s.mode == GSQL_XCHG_BROADCAST) {
-                int64_t g = div_up(X.rows, 256);
-                if (g > (int64_t)ctx->sm_count * 4) g = (int64_t)ctx->sm_count * 4;
-                k_xchg_bcast<<<(int)g, 256, 0, ps>>>(PP);
-            } else {
-                k_xchg_push<<<X.nblocks, PUSH_THREADS, 0, ps>>>(PP);
+            {
+                KernelScope ks(ctx, s.mode == GSQL_XCHG_BROADCAST ? "xchg_bcast" : "xchg_push", ps);
+                if (s.mode == GSQL_XCHG_BROADCAST) {
+                    int64_t g = div_up(X.rows, 256);
+                    if (g > (int64_t)ctx->sm_count * 4) g = (int64_t)ctx->sm_count * 4;
+                    k_xchg_bcast<<<(int)g, 256, 0, ps>>>(PP);
+                } else {
+                    bool plain = s.n_cols <= 4;  // register-prefetch variant: few columns, none of them nullable
+                    for (int c = 0; c < s.n_cols; c++) plain = plain && x->null_off[c] < 0;
+                    const bool fast = push_fast_key(X);
+#define GSQL_PUSH_CASE(F, NCv) k_xchg_push<F, NCv><<<X.nblocks, PUSH_THREADS, 0, ps>>>(PP)
+                    const int nc = plain ? s.n_cols : 0;
+                    if (fast) {
+                        switch (nc) {
+                        case 1: GSQL_PUSH_CASE(true, 1); break;
+                        case 2: GSQL_PUSH_CASE(true, 2); break;
+                        case 3: GSQL_PUSH_CASE(true, 3); break;
+                        case 4: GSQL_PUSH_CASE(true, 4); break;
+                        default: GSQL_PUSH_CASE(true, 0); break;
+                        }
+                    } else {
+                        switch (nc) {
+                        case 1: GSQL_PUSH_CASE(false, 1); break;
+                        case 2: GSQL_PUSH_CASE(false, 2); break;
+                        case 3: GSQL_PUSH_CASE(false, 3); break;
+                        case 4: GSQL_PUSH_CASE(false, 4); break;
+                        default: GSQL_PUSH_CASE(false, 0); break;
+                        }
+                    }
+#undef GSQL_PUSH_CASE
+                }
             }
             GSQL_CUDA(ctx, cudaGetLastError());
         }

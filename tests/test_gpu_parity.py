@@ -550,10 +550,14 @@ def test_agg_low_cardinality_paths_agree_with_oracle(gu, monkeypatch, path, ngro
         gu.approx_rows_equal(got, exp, float_cols=[nk + 3, nk + 4, nk + 5, nk + 9], key_cols=list(range(nk)), rtol=RTOL)
 
 
-def test_agg_lane_kernel_is_taken_for_q1_shape(gu):
-    """The Q1 shape (6 groups, 8 aggregates over plain DOUBLE columns) runs on k_agg_lane: the context's kernel profile
-    shows it, and no row leaves it for the generic path."""
+@pytest.mark.parametrize("kernel", ["reg", "lane"])
+def test_agg_privatised_kernel_is_taken_for_q1_shape(gu, monkeypatch, kernel):
+    """The Q1 shape (6 groups, aggregates over plain DOUBLE columns, no NULLs) runs on k_agg_reg (register accumulators);
+    with that kernel switched off, on k_agg_lane.  The context's kernel profile shows which, and no row leaves for the
+    generic kernel."""
     from galaxysql_b200 import api, native as N
+    if kernel == "lane":
+        monkeypatch.setenv("GSQL_AGG_NO_REG", "1")
     n = 500_000
     flag = (ku.rand_u64(n, 41) % np.uint64(3)).astype(np.int32)
     status = (ku.rand_u64(n, 42) % np.uint64(2)).astype(np.int32)
@@ -570,10 +574,69 @@ def test_agg_lane_kernel_is_taken_for_q1_shape(gu):
     a.close()
     prof = ctx.profile_dump()
     ctx.profile(False)
-    assert "agg_lane" in prof and "agg_smem" not in prof and "agg_consume" not in prof, prof
+    assert "agg_" + kernel in prof and "agg_smem" not in prof and "agg_consume" not in prof, prof
     oaggs = [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_AVG, [2]), orc.AggCall(orc.AGG_AVG, [3]),
              orc.AggCall(orc.AGG_COUNT_STAR)]
     gu.approx_rows_equal(got, orc.hash_agg(cols, [0, 1], oaggs, 8), float_cols=[2, 3, 4, 5], key_cols=[0, 1], rtol=RTOL)
+
+
+@pytest.mark.parametrize("shape", ["q1_fused", "one_bigint_key", "thirteen_groups", "count_only_plus_sum"])
+def test_agg_reg_kernel_shapes_vs_oracle(gu, shape):
+    """k_agg_reg on its edge shapes: the full Q1 plan (2 INT keys, 5 distinct fp64 sums incl. both fused expressions, the
+    shipdate filter, 3 batches), one BIGINT key with negative values, 13 groups (more than a block's registers hold: the
+    surplus rows take the in-kernel generic path, then the handle adapts), COUNT(x) folded into the row counter."""
+    from galaxysql_b200 import api, native as N
+    n = 1_200_003
+    price = ((ku.rand_u64(n, 54) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    disc = (ku.rand_u64(n, 55) % np.uint64(11)).astype(np.float64) / 100.0
+    tax = (ku.rand_u64(n, 56) % np.uint64(9)).astype(np.float64) / 100.0
+    qty = ((ku.rand_u64(n, 53) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
+    ship = ((ku.rand_u64(n, 57) % np.uint64(2526)) + np.uint64(8036)).astype(np.int32)
+    derived, row_filter, mask = (), None, np.ones(n, bool)
+    if shape == "q1_fused":
+        keys = [(ku.rand_u64(n, 51) % np.uint64(3)).astype(np.int32), (ku.rand_u64(n, 52) % np.uint64(2)).astype(np.int32)]
+        derived = [(N.EXPR_MUL_1MINUS, 3, 4, 0), (N.EXPR_MUL_1MINUS_1PLUS, 3, 4, 5)]
+        row_filter = (6, N.CMP_LE, 10471)
+        mask = ship <= 10471
+    elif shape == "one_bigint_key":
+        keys = [(ku.rand_u64(n, 51) % np.uint64(7)).astype(np.int64) * 3_000_000_007 - 9_000_000_000]
+    elif shape == "thirteen_groups":
+        keys = [(ku.rand_u64(n, 51) % np.uint64(13)).astype(np.int32) - 6, np.zeros(n, dtype=np.int32)]
+    else:
+        keys = [(ku.rand_u64(n, 51) % np.uint64(5)).astype(np.int32)]
+    nk = len(keys)
+    cols = [(k, None) for k in keys] + [(qty, None), (price, None), (disc, None), (tax, None), (ship, None)]
+    types = [N.T_INT32 if k.dtype == np.int32 else N.T_INT64 for k in keys] + [2, 2, 2, 2, 0]
+    q, pr, di, tx = nk, nk + 1, nk + 2, nk + 3
+    ncol = len(cols)
+    if shape == "q1_fused":
+        derived = [(N.EXPR_MUL_1MINUS, pr, di, 0), (N.EXPR_MUL_1MINUS_1PLUS, pr, di, tx)]
+        row_filter = (nk + 4, N.CMP_LE, 10471)
+        aggs = [(N.AGG_SUM, [q]), (N.AGG_SUM, [pr]), (N.AGG_SUM, [ncol]), (N.AGG_SUM, [ncol + 1]), (N.AGG_AVG, [q]), (N.AGG_AVG, [pr]),
+                (N.AGG_AVG, [di]), (N.AGG_COUNT_STAR, [])]
+    elif shape == "count_only_plus_sum":
+        aggs = [(N.AGG_COUNT, [q, pr]), (N.AGG_SUM, [q]), (N.AGG_COUNT_STAR, [])]
+    else:
+        aggs = [(N.AGG_SUM, [q]), (N.AGG_AVG, [pr]), (N.AGG_COUNT_STAR, []), (N.AGG_SUM, [di])]
+    ctx = gu.ctx()
+    ctx.profile(True)
+    ctx.profile_reset()
+    a = api.HashAgg(ctx, types, list(range(nk)), aggs, 16, derived=derived, row_filter=row_filter)
+    edges = [0, 400_000, 400_001, n]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        a.consume(gu.to_device([(d[lo:hi], None) for d, _ in cols]))
+    got = gu.to_numpy(a.result(N.MEM_DEVICE))
+    a.close()
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    assert "agg_reg" in prof, prof
+    e1 = price * (1.0 - disc)
+    e2 = e1 * (1.0 + tax)
+    ocols = [(c[0][mask], None) for c in cols] + [(e1[mask], None), (e2[mask], None)]
+    okind = {N.AGG_SUM: orc.AGG_SUM, N.AGG_AVG: orc.AGG_AVG, N.AGG_COUNT_STAR: orc.AGG_COUNT_STAR, N.AGG_COUNT: orc.AGG_COUNT}
+    exp = orc.hash_agg(ocols, list(range(nk)), [orc.AggCall(okind[k], c) for k, c in aggs], 16)
+    fcols = [nk + i for i, (k, _) in enumerate(aggs) if k in (N.AGG_SUM, N.AGG_AVG)]
+    gu.approx_rows_equal(got, exp, float_cols=fcols, key_cols=list(range(nk)), rtol=RTOL)
 
 
 def test_agg_partition_prepass_opt_in(gu, monkeypatch):
