@@ -18,6 +18,7 @@
 
 #include <algorithm>
 
+#include <cooperative_groups.h>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -141,7 +142,13 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
             else cur = prev;
         }
         if (mine) {  // first appearance: allocate the dense group id, publish keys, then the id
-            int gid = (int)atomicAdd(&P.counters[C_NGROUPS], 1ULL);
+            // the lanes that create a group in the same step share ONE bump of the group counter (a first batch of millions
+            // of new groups used to serialise on that single L2 address: 4.9 ms for 4.5 M groups in the Q3 aggregation)
+            cooperative_groups::coalesced_group cg = cooperative_groups::coalesced_threads();
+            unsigned long long gbase = 0;
+            if (cg.thread_rank() == 0) gbase = atomicAdd(&P.counters[C_NGROUPS], (unsigned long long)cg.size());
+            gbase = cg.shfl(gbase, 0);
+            int gid = (int)gbase + (int)cg.thread_rank();
             if ((int64_t)gid >= P.garr) {  // cannot happen while the host grows after every launch (slack covers one launch's merges):
                 P.counters[C_FATAL] = 1;   // never write out of bounds — the host turns this into an error
                 gid = (int)(P.garr - 1);
@@ -180,15 +187,15 @@ __device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
     return find_group_kv(P, kv, kn, d);
 }
 
-__device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {
-    if (c.type == GSQL_T_INT32) return reinterpret_cast<const int32_t *>(c.data)[r];
-    if (c.type == GSQL_T_INT64) return reinterpret_cast<const int64_t *>(c.data)[r];
-    return (int64_t) reinterpret_cast<const double *>(c.data)[r];
+__device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {  // streaming (evict-first) reads: every input value is used once
+    if (c.type == GSQL_T_INT32) return __ldcs(reinterpret_cast<const int *>(c.data) + r);
+    if (c.type == GSQL_T_INT64) return __ldcs(reinterpret_cast<const long long *>(c.data) + r);
+    return (int64_t)__ldcs(reinterpret_cast<const double *>(c.data) + r);
 }
 __device__ __forceinline__ double in_f64(const DCol &c, int64_t r) {
-    if (c.type == GSQL_T_FP64) return reinterpret_cast<const double *>(c.data)[r];
-    if (c.type == GSQL_T_INT64) return (double)reinterpret_cast<const int64_t *>(c.data)[r];
-    return (double)reinterpret_cast<const int32_t *>(c.data)[r];
+    if (c.type == GSQL_T_FP64) return __ldcs(reinterpret_cast<const double *>(c.data) + r);
+    if (c.type == GSQL_T_INT64) return (double)__ldcs(reinterpret_cast<const long long *>(c.data) + r);
+    return (double)__ldcs(reinterpret_cast<const int *>(c.data) + r);
 }
 
 // Column `col` of row r as the aggregators see it: a plain input column, or a fused derived expression
@@ -256,12 +263,12 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
             long long carry = (sum < old ? 1 : 0) + (v < 0 ? -1 : 0);
             if (carry) atomicAdd(reinterpret_cast<unsigned long long *>(&a.hi[gid]), (unsigned long long)carry);
         }
-        a.has[gid] = 1;
+        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_AVG:
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
-        a.has[gid] = 1;
+        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_SUM0:
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, c, r));
@@ -269,7 +276,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     case GSQL_AGG_AVG_MERGE:  // (partial sum, partial count): the sum is NULL exactly when its count is 0
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         if (!val_null(P, a.cols[1], r)) atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, a.cols[1], r));
-        a.has[gid] = 1;
+        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_MIN:
     case GSQL_AGG_MAX: {
@@ -277,7 +284,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
         long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(val_f64(P, c, r), mx) : val_i64(P, c, r);
         if (mx) atomicMax(reinterpret_cast<long long *>(&a.l[gid]), v);
         else atomicMin(reinterpret_cast<long long *>(&a.l[gid]), v);
-        a.has[gid] = 1;
+        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     }
     default: return;
@@ -712,6 +719,25 @@ static gsql_status agg_read_counters(gsql_agg *a, unsigned long long *h) {
 // columns, which live in `bufs` until the caller returns.
 static gsql_status agg_partition_batch(gsql_agg *a, StagedBatch *sb, int nparts, DevBuf *bufs, DevBuf *nbufs) {
     gsql_ctx *ctx = a->ctx;
+    {  // the C5 shape — one integer key, a few NULL-free columns — goes through the warp-synchronous split kernels of the
+       // push exchange (xchg.cu); r02 measured the scalar scatter below at 7.8 ms per 250 M rows (latency-bound, 20 % issue)
+        bool plain = a->nkeys == 1 && sb->ncols <= 4 && nparts <= GSQL_MAX_RANKS && sb->cols[a->spec.groups[0]].type != GSQL_T_FP64;
+        for (int c = 0; c < sb->ncols; c++) plain = plain && sb->cols[c].nulls == nullptr;
+        if (plain) {
+            DColSet in;
+            memset(&in, 0, sizeof(in));
+            in.n = sb->ncols;
+            void *out[GSQL_MAX_COLS];
+            for (int c = 0; c < sb->ncols; c++) {
+                in.c[c] = sb->cols[c];
+                GSQL_TRY(bufs[c].alloc(ctx, (size_t)sb->rows * gsql_type_width(sb->cols[c].type)));
+                out[c] = bufs[c].p;
+            }
+            GSQL_TRY(local_split_by_slot_range(ctx, in, a->spec.groups[0], sb->rows, nparts, out));
+            for (int c = 0; c < sb->ncols; c++) sb->cols[c].data = out[c];
+            return GSQL_OK;
+        }
+    }
     AggParams P;
     agg_fill_params(a, sb, &P);
     P.row0 = 0;
@@ -792,6 +818,8 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         int64_t slice = getenv("GSQL_AGG_PARTITION_BYTES") ? atoll(getenv("GSQL_AGG_PARTITION_BYTES")) : (16ll << 20);
         if (part_on && generic && a->nkeys > 0 && batch->rows >= min_rows && table_bytes > 4 * slice) {
             int64_t nparts = div_up(table_bytes, slice);
+            // up to 16 partitions the fast split kernels apply: prefer somewhat larger slices (<= 32 MB) to the scalar scatter
+            if (nparts > GSQL_MAX_RANKS && div_up(table_bytes, GSQL_MAX_RANKS) <= 2 * slice) nparts = GSQL_MAX_RANKS;
             if (nparts > 4096) nparts = 4096;
             GSQL_TRY(agg_partition_batch(a, &sb, (int)nparts, part_data, part_nulls));
         }
@@ -814,17 +842,25 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         const bool use_smem = !use_reg && !use_lane && first && a->fast.eligible && a->fast.enabled;
         if (use_reg) {  // register accumulators: NULL-free batch, <= 8 groups, fp64 sums (the Q1 shape)
             KernelScope ks(ctx, "agg_reg");
-            int64_t tiles = div_up(P.rows, RG_THREADS * RG_RPT);
-            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * 2, tiles);
+            int64_t tiles = div_up(P.rows, RG_TILE);
+            const size_t smem = (size_t)2 * RP.tile_bytes;
+            const int per_sm = smem * 2 + 16384 <= 220 * 1024 ? 2 : 1;
+            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, tiles);
             if (grid < 1) grid = 1;
+#define GSQL_REG_CASE(NS, GG)                                                                                              \
+    {                                                                                                                      \
+        GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_reg<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        k_agg_reg<NS, GG><<<grid, RG_THREADS, smem, ctx->stream>>>(P, RP);                                                 \
+    }
             switch (RP.nsrc) {
-            case 1: k_agg_reg<1, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
-            case 2: k_agg_reg<2, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
-            case 3: k_agg_reg<3, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
-            case 4: k_agg_reg<4, 8><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
-            case 5: k_agg_reg<5, 6><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
-            default: k_agg_reg<6, 6><<<grid, RG_THREADS, 0, ctx->stream>>>(P, RP); break;
+            case 1: GSQL_REG_CASE(1, 8) break;
+            case 2: GSQL_REG_CASE(2, 8) break;
+            case 3: GSQL_REG_CASE(3, 8) break;
+            case 4: GSQL_REG_CASE(4, 8) break;
+            case 5: GSQL_REG_CASE(5, 6) break;
+            default: GSQL_REG_CASE(6, 6) break;
             }
+#undef GSQL_REG_CASE
         } else if (use_lane) {
             KernelScope ks(ctx, "agg_lane");
             int64_t steps = div_up(P.rows, 32 * LA_R * LA_WARPS);

@@ -6,9 +6,11 @@
 // at 12.3 warp-instructions per ROW (~390 thread instructions) and 21 % issue utilisation: 22.5 ms for the 26.4 GB of
 // config 3, 18 % of the HBM roofline.  Here a thread owns RG_G x NSRC fp64 accumulators and RG_G counters in REGISTERS;
 // a row costs its loads, one compare per group and NSRC predicated DADDs per group — ~100 thread instructions with
-// NSRC x RG_G independent dependency chains — and no shared-memory traffic at all in steady state.  The (at most RG_G)
-// group keys live in a per-block dictionary in shared memory that is only written when a new key shows up (the first
-// tiles); a ninth key makes the row take the generic path on the spot (find_group_kv + L2 atomics), counted in
+// NSRC x RG_G independent dependency chains.  The input columns of a tile reach shared memory through cp.async, one tile
+// ahead of the accumulation (double buffer), so the HBM latency of the stream is never on a thread's critical path and no
+// register holds a load in flight.  The (at most RG_G) group keys live in a per-block dictionary in shared memory that is
+// only written when a new key shows up (the first tiles; warp-cooperative under a block lock, no block barrier in the row
+// loop); a ninth key makes the row take the generic path on the spot (find_group_kv + L2 atomics), counted in
 // C_FALLBACK so that the host stops choosing this kernel when that is common.  Everything that depends on the plan —
 // the number of sums, the expression kind of each — is a template parameter or a warp-uniform branch on a
 // __grid_constant__ descriptor; nothing is interpreted per row.
@@ -23,41 +25,75 @@
 namespace {
 
 constexpr int RG_THREADS = 256;
-constexpr int RG_RPT = 2;       // rows per thread per tile: all loads of both rows are in flight together
+constexpr int RG_RPT = 4;       // rows per thread per tile
+constexpr int RG_TILE = RG_THREADS * RG_RPT;
 constexpr int RG_G = 8;         // groups a block can hold in registers (6 when there are 5-6 sums: 128 registers, two blocks per SM, no spills)
 constexpr int RG_MAX_SRC = 6;   // distinct fp64 sums
+constexpr int RG_MAX_USED = 8;  // distinct input columns a tile stages
 
 struct RegSrc {
-    int32_t kind;  // 0: column a; GSQL_EXPR_MUL_1MINUS: a*(1-b); GSQL_EXPR_MUL_1MINUS_1PLUS: a*(1-b)*(1+c)
-    int32_t a, b, c;
+    int32_t kind;        // 0: column a; GSQL_EXPR_MUL_1MINUS: a*(1-b); GSQL_EXPR_MUL_1MINUS_1PLUS: a*(1-b)*(1+c)
+    int32_t ua, ub, uc;  // staged-column slots
+    int32_t oa, ob, oc;  // byte offsets of the operands' regions inside a tile buffer (host-flattened: with the source index a
+    int32_t pad;         // compile-time constant after unrolling, these are direct constant-bank operands, no table walk)
 };
 
 struct RegPlan {
-    int32_t nsrc, nkeys;
+    int32_t nsrc, nkeys, nused, tile_bytes;
     RegSrc src[RG_MAX_SRC];
-    int32_t keycol[2];
+    int32_t used_col[RG_MAX_USED];   // input column of each staged slot
+    int32_t used_off[RG_MAX_USED];   // byte offset of the slot's RG_TILE elements inside a tile buffer
+    int32_t used_w[RG_MAX_USED];     // 4 or 8
+    int32_t key_u[2];
+    int32_t key_off[2], key_w[2];    // flattened copies for the row loop
+    int32_t rf_u;                    // slot of the row-filter column, -1: no filter
+    int32_t rf_off, rf_w, rf_neg;    // the filter as an interval test: pass = (lo <= x && x <= hi) != neg
+    int64_t rf_lo, rf_hi;
     int32_t agg_src[GSQL_MAX_AGGS];  // per aggregate: the sum it reports, -1 for COUNT / COUNT(*)
 };
 
-__device__ __forceinline__ double reg_f64(const DCol &c, int64_t r) { return __longlong_as_double(ld_stream_8(reinterpret_cast<const long long *>(c.data) + r)); }
+__device__ __forceinline__ void rg_cp_async_4(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void rg_cp_async_8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void rg_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void rg_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ double reg_src(const AggParams &P, const RegSrc &s, int64_t r) {
-    double x = reg_f64(P.in.c[s.a], r);
-    if (s.kind != 0) {  // warp-uniform
-        x = x * (1.0 - reg_f64(P.in.c[s.b], r));
-        if (s.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) x = x * (1.0 + reg_f64(P.in.c[s.c], r));
+// Asynchronous copy (LDGSTS) of one tile's staged columns into `buf`: element (k * RG_THREADS + tid) of every column is
+// copied — and later read back — by the same thread, so no block barrier is needed, only the thread's own wait_group.
+__device__ __forceinline__ void rg_prefetch(const AggParams &P, const RegPlan &L, int64_t t0, unsigned char *buf) {
+    const int tid = threadIdx.x;
+    const int64_t left = P.rows - t0;
+#pragma unroll 1
+    for (int u = 0; u < L.nused; u++) {
+        const DCol &c = P.in.c[L.used_col[u]];
+        unsigned char *dst = buf + L.used_off[u];
+        if (L.used_w[u] == 4) {
+            const int *src = reinterpret_cast<const int *>(c.data) + P.row0 + t0;
+#pragma unroll
+            for (int k = 0; k < RG_RPT; k++) {
+                const int i = k * RG_THREADS + tid;
+                if (i < left) rg_cp_async_4(dst + (size_t)i * 4, src + i);
+            }
+        } else {
+            const long long *src = reinterpret_cast<const long long *>(c.data) + P.row0 + t0;
+#pragma unroll
+            for (int k = 0; k < RG_RPT; k++) {
+                const int i = k * RG_THREADS + tid;
+                if (i < left) rg_cp_async_8(dst + (size_t)i * 8, src + i);
+            }
+        }
     }
-    return x;
+    rg_cp_async_commit();
 }
 
-__device__ __forceinline__ unsigned long long reg_key(const AggParams &P, const RegPlan &L, int64_t r) {
-    unsigned long long k = 0;
-    const DCol &c0 = P.in.c[L.keycol[0]];
-    if (c0.type == GSQL_T_INT32) k = (unsigned long long)(unsigned int)ld_stream_4(reinterpret_cast<const int *>(c0.data) + r);
-    else k = (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(c0.data) + r);
-    if (L.nkeys == 2)  // two INT keys share the word (checked on the host)
-        k |= (unsigned long long)(unsigned int)ld_stream_4(reinterpret_cast<const int *>(P.in.c[L.keycol[1]].data) + r) << 32;
-    return k;
+// acc += v when gk == G0 — one ISETP and one predicated DADD (the `hit ? v : 0.0` form compiles to two FSELs and a DADD)
+template <int G0>
+__device__ __forceinline__ void rg_pred_add(double &acc, double v, int gk) {
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"(gk), "n"(G0));
 }
 
 __device__ __forceinline__ void reg_decode_key(const AggParams &P, const RegPlan &L, unsigned long long k, int64_t (&kv)[GSQL_MAX_KEYS], bool (&kn)[GSQL_MAX_KEYS]) {
@@ -66,18 +102,29 @@ __device__ __forceinline__ void reg_decode_key(const AggParams &P, const RegPlan
         kv[0] = (int64_t)(int32_t)(unsigned int)k;
         kv[1] = (int64_t)(int32_t)(unsigned int)(k >> 32);
     } else {
-        kv[0] = P.in.c[L.keycol[0]].type == GSQL_T_INT32 ? (int64_t)(int32_t)(unsigned int)k : (int64_t)k;
+        kv[0] = L.key_w[0] == 4 ? (int64_t)(int32_t)(unsigned int)k : (int64_t)k;
+    }
+}
+
+template <int NSRC, int G, int G0>
+__device__ __forceinline__ void rg_accumulate(double (&acc)[G][NSRC], unsigned int (&cnt)[G], const double (&v)[NSRC], int gk) {
+    if constexpr (G0 < G) {
+        cnt[G0] += gk == G0 ? 1u : 0u;
+#pragma unroll
+        for (int j = 0; j < NSRC; j++) rg_pred_add<G0>(acc[G0][j], v[j], gk);
+        rg_accumulate<NSRC, G, G0 + 1>(acc, cnt, v, gk);
     }
 }
 
 template <int NSRC, int G>
 __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant__ AggParams P, const __grid_constant__ RegPlan L) {
+    extern __shared__ __align__(16) unsigned char rg_smem[];  // two tile buffers
     __shared__ unsigned long long skey[G];
-    __shared__ int s_ng, s_elect;
+    __shared__ int s_ng, s_lock;
     __shared__ double red[RG_THREADS / 32][G][NSRC];
     __shared__ unsigned long long redc[RG_THREADS / 32][G];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_ng = 0; s_elect = 0x7fffffff; }
+    if (tid == 0) { s_ng = 0; s_lock = 0; }
     double acc[G][NSRC];
     unsigned int cnt[G];
 #pragma unroll
@@ -88,62 +135,86 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant
     }
     __syncthreads();
     unsigned long long fallback_rows = 0;
-    constexpr int TILE = RG_THREADS * RG_RPT;
-    const int64_t ntiles = (P.rows + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t t0 = tile * TILE;
-        unsigned long long key[RG_RPT];
-        double v[RG_RPT][NSRC];
-        bool pass[RG_RPT];
-        // ---- every load of the tile is issued before anything is consumed
-#pragma unroll
-        for (int k = 0; k < RG_RPT; k++) {
-            const int64_t i = t0 + k * RG_THREADS + tid;
-            pass[k] = i < P.rows;
-            const int64_t r = P.row0 + (pass[k] ? i : 0);
-            key[k] = reg_key(P, L, r);
-#pragma unroll
-            for (int j = 0; j < NSRC; j++) v[k][j] = reg_src(P, L.src[j], r);
-            if (pass[k] && P.rf_op != GSQL_CMP_NONE) pass[k] = row_passes(P, r);
-        }
-        // ---- group of each row: position of its key in the block's dictionary
-        int gid[RG_RPT];
-        while (true) {
-            const int ng = s_ng;
-            bool miss = false;
-#pragma unroll
-            for (int k = 0; k < RG_RPT; k++) {
-                gid[k] = -1;
+    const int64_t ntiles = (P.rows + RG_TILE - 1) / RG_TILE;
+    int64_t tile = blockIdx.x;
+    if (tile < ntiles) rg_prefetch(P, L, tile * RG_TILE, rg_smem);
+    unsigned long long kk[G];  // this thread's copy of the block's key dictionary
+    int ng = 0;
+    for (int it = 0; tile < ntiles; tile += gridDim.x, it++) {
+        const int64_t t0 = tile * RG_TILE;
+        const int64_t next = tile + gridDim.x;
+        // the next tile's columns start their way from HBM before this tile is touched: the memory latency of the stream
+        // is hidden behind the accumulation of a whole tile instead of being paid once per tile
+        if (next < ntiles) rg_prefetch(P, L, next * RG_TILE, rg_smem + (size_t)((it + 1) & 1) * L.tile_bytes);
+        else rg_cp_async_commit();
+        rg_cp_async_wait<1>();
+        const unsigned char *buf = rg_smem + (size_t)(it & 1) * L.tile_bytes;
+        const int64_t left = P.rows - t0;
+        {  // refresh the register copy of the dictionary when another warp has added keys
+            const int now = *reinterpret_cast<volatile int *>(&s_ng);
+            if (now != ng) {
 #pragma unroll
                 for (int g = 0; g < G; g++)
-                    if (g < ng && skey[g] == key[k]) gid[k] = g;
-                miss |= pass[k] && gid[k] < 0;
+                    if (g < now) kk[g] = *reinterpret_cast<volatile unsigned long long *>(&skey[g]);
+                ng = now;
             }
-            const bool room = ng < G;
-            if (!__syncthreads_or(miss && room)) break;  // steady state: one barrier per tile, no dictionary write
-            if (miss) atomicMin(&s_elect, tid);
-            __syncthreads();
-            if (tid == s_elect) {  // one new key per round (first tiles only)
-                unsigned long long nk = 0;
-#pragma unroll
-                for (int k = RG_RPT - 1; k >= 0; k--)
-                    if (pass[k] && gid[k] < 0) nk = key[k];
-                skey[s_ng] = nk;
-                s_ng = s_ng + 1;
-                s_elect = 0x7fffffff;
-            }
-            __syncthreads();
         }
-        // ---- accumulate: one compare per group, NSRC predicated adds
-        const int ng = s_ng;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < RG_RPT; k++) {
-            if (pass[k] && gid[k] < 0) {  // a ninth key: the generic path, right here
+            const int i = k * RG_THREADS + tid;
+            bool pass = i < left;
+            const unsigned char *row8 = buf + (size_t)i * 8, *row4 = buf + (size_t)i * 4;
+            unsigned long long key = L.key_w[0] == 4 ? (unsigned long long)*reinterpret_cast<const unsigned int *>(row4 + L.key_off[0])
+                                                     : *reinterpret_cast<const unsigned long long *>(row8 + L.key_off[0]);
+            if (L.nkeys == 2) key |= (unsigned long long)*reinterpret_cast<const unsigned int *>(row4 + L.key_off[1]) << 32;
+            if (L.rf_u >= 0) {  // fused scan-side predicate as an interval test (NULL-free column: checked by the plan)
+                const long long x = L.rf_w == 4 ? (long long)*reinterpret_cast<const int *>(row4 + L.rf_off) : *reinterpret_cast<const long long *>(row8 + L.rf_off);
+                pass = pass && ((x >= L.rf_lo && x <= L.rf_hi) != (L.rf_neg != 0));
+            }
+            int gid = -1;
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (g < ng && kk[g] == key) gid = g;
+            // ---- a key this thread has not seen: add it to the block's dictionary (first tiles only); warp-cooperative, one
+            // distinct key at a time, lane 0 takes the block's lock — no block barrier anywhere in the row loop
+            unsigned need = __ballot_sync(0xffffffffu, pass && gid < 0);
+            while (need) {
+                const int leader = __ffs(need) - 1;
+                const unsigned long long lk = __shfl_sync(0xffffffffu, key, leader);
+                int got = -1;
+                if (lane == 0) {
+                    while (atomicCAS(&s_lock, 0, 1) != 0) {}
+                    const int cur = *reinterpret_cast<volatile int *>(&s_ng);
+                    for (int g = 0; g < cur; g++)
+                        if (*reinterpret_cast<volatile unsigned long long *>(&skey[g]) == lk) got = g;
+                    if (got < 0 && cur < G) {
+                        *reinterpret_cast<volatile unsigned long long *>(&skey[cur]) = lk;
+                        __threadfence_block();
+                        *reinterpret_cast<volatile int *>(&s_ng) = cur + 1;
+                        got = cur;
+                    } else if (got < 0) {
+                        got = -2;  // the dictionary is full: these rows take the generic path
+                    }
+                    __threadfence_block();
+                    atomicExch(&s_lock, 0);
+                }
+                got = __shfl_sync(0xffffffffu, got, 0);
+                if (pass && gid < 0 && key == lk) gid = got;
+                if (got >= 0) {  // every lane learns the new entry
+                    const int now = *reinterpret_cast<volatile int *>(&s_ng);
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if (g < now) kk[g] = *reinterpret_cast<volatile unsigned long long *>(&skey[g]);
+                    ng = now;
+                }
+                need = __ballot_sync(0xffffffffu, pass && gid == -1);
+            }
+            if (pass && gid == -2) {  // a ninth key: the generic path, right here
                 fallback_rows++;
                 int64_t kv[GSQL_MAX_KEYS];
                 bool kn[GSQL_MAX_KEYS];
-                reg_decode_key(P, L, key[k], kv, kn);
-                const int64_t r = P.row0 + t0 + k * RG_THREADS + tid;
+                reg_decode_key(P, L, key, kv, kn);
+                const int64_t r = P.row0 + t0 + i;
                 const int g2 = find_group_kv(P, kv, kn, digest_of_keys(P, kv, kn));
                 if (g2 < 0) {
                     unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
@@ -151,46 +222,54 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant
                 } else {
                     for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], g2, r);
                 }
-                continue;
+                pass = false;
             }
-            const int gk = pass[k] ? gid[k] : -1;
+            // ---- accumulate: the row's values come out of shared memory (a dead row reads its own, in-buffer cell and is
+            // masked by gk = -1), one compare per group, NSRC predicated adds
+            double v[NSRC];
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                if (g >= 4 && ng <= 4) break;  // block-uniform: dbgen's Q1 has 4 groups
-                const bool hit = gk == g;
-                cnt[g] += hit ? 1u : 0u;
-#pragma unroll
-                for (int j = 0; j < NSRC; j++) acc[g][j] += hit ? v[k][j] : 0.0;
+            for (int j = 0; j < NSRC; j++) {
+                const RegSrc &sr = L.src[j];
+                double x = *reinterpret_cast<const double *>(row8 + sr.oa);
+                if (sr.kind != 0) {  // block-uniform
+                    x = x * (1.0 - *reinterpret_cast<const double *>(row8 + sr.ob));
+                    if (sr.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) x = x * (1.0 + *reinterpret_cast<const double *>(row8 + sr.oc));
+                }
+                v[j] = x;
             }
+            const int gk = pass ? gid : -1;
+            rg_accumulate<NSRC, G, 0>(acc, cnt, v, gk);
         }
     }
+    rg_cp_async_wait<0>();
     if (fallback_rows) atomicAdd(&P.counters[C_FALLBACK], fallback_rows);
     // ---- merge: reduce over the warp with shuffles, over the block through shared memory, then one thread per group
-    const int ng = s_ng;
+    __syncthreads();
+    const int ngf = s_ng;
 #pragma unroll
     for (int g = 0; g < G; g++) {
-        if (g >= ng) break;
+        if (g >= ngf) break;
         unsigned int c = cnt[g];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
         if (lane == 0) redc[warp][g] = c;
 #pragma unroll
         for (int j = 0; j < NSRC; j++) {
-            const double s = warp_sum_f64(acc[g][j]);
-            if (lane == 0) red[warp][g][j] = s;
+            const double sm = warp_sum_f64(acc[g][j]);
+            if (lane == 0) red[warp][g][j] = sm;
         }
     }
     __syncthreads();
-    if (tid < ng) {
+    if (tid < ngf) {
         const int g = tid;
         unsigned long long c = 0;
-        double s[NSRC];
+        double sums[NSRC];
 #pragma unroll
-        for (int j = 0; j < NSRC; j++) s[j] = 0.0;
+        for (int j = 0; j < NSRC; j++) sums[j] = 0.0;
         for (int w = 0; w < RG_THREADS / 32; w++) {
             c += redc[w][g];
 #pragma unroll
-            for (int j = 0; j < NSRC; j++) s[j] += red[w][g][j];
+            for (int j = 0; j < NSRC; j++) sums[j] += red[w][g][j];
         }
         if (c) {  // (a key whose rows all failed the filter never entered the dictionary)
             int64_t kv[GSQL_MAX_KEYS];
@@ -203,7 +282,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant
                 double sv = 0.0;
 #pragma unroll
                 for (int j = 0; j < NSRC; j++)
-                    if (L.agg_src[a] == j) sv = s[j];
+                    if (L.agg_src[a] == j) sv = sums[j];
                 switch (ag.kind) {
                 case GSQL_AGG_COUNT_STAR: case GSQL_AGG_COUNT:
                     atomicAdd(reinterpret_cast<unsigned long long *>(&ag.l[gl]), c);
@@ -261,12 +340,25 @@ static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int 
     RegPlan &L = *Lp;
     memset(&L, 0, sizeof(L));
     L.nkeys = nkeys;
+    L.rf_u = -1;
     auto has_nulls = [&](int col) { return in.c[col].nulls != nullptr; };
+    bool too_many = false;
+    auto slot_of = [&](int col) -> int {  // staged slot of an input column
+        for (int u = 0; u < L.nused; u++)
+            if (L.used_col[u] == col) return u;
+        if (L.nused == RG_MAX_USED) { too_many = true; return 0; }
+        L.used_col[L.nused] = col;
+        L.used_w[L.nused] = in.c[col].type == GSQL_T_INT32 ? 4 : 8;
+        return L.nused++;
+    };
     for (int k = 0; k < nkeys; k++) {
-        L.keycol[k] = spec.groups[k];
         if (has_nulls(spec.groups[k])) return false;
+        L.key_u[k] = slot_of(spec.groups[k]);
     }
-    if (spec.row_filter_op != GSQL_CMP_NONE && has_nulls(spec.row_filter_col)) return false;
+    if (spec.row_filter_op != GSQL_CMP_NONE) {
+        if (has_nulls(spec.row_filter_col)) return false;
+        L.rf_u = slot_of(spec.row_filter_col);
+    }
     for (int a = 0; a < naggs; a++) {
         L.agg_src[a] = -1;
         const gsql_agg_call &c = aggs[a];
@@ -282,21 +374,25 @@ static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int 
             continue;
         }
         if (c.kind == GSQL_AGG_COUNT_STAR) continue;
-        RegSrc s;
+        int kind = 0, oa, ob = 0, oc = 0;
         const int col = c.cols[0];
         if (col < spec.n_input_cols) {
-            s.kind = 0; s.a = col; s.b = s.c = 0;
-            if (has_nulls(col) || in.c[col].type != GSQL_T_FP64) return false;
+            oa = col;
         } else {
             const gsql_derived_col &d = spec.derived[col - spec.n_input_cols];
-            s.kind = d.kind; s.a = d.a; s.b = d.b; s.c = d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS ? d.c : 0;
-            const int ops[3] = {s.a, s.b, s.c};
-            for (int q = 0; q < (d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS ? 3 : 2); q++)
-                if (has_nulls(ops[q]) || in.c[ops[q]].type != GSQL_T_FP64) return false;
+            kind = d.kind; oa = d.a; ob = d.b; oc = d.kind == GSQL_EXPR_MUL_1MINUS_1PLUS ? d.c : d.b;
         }
+        const int ops[3] = {oa, ob, oc};
+        for (int q = 0; q < (kind == 0 ? 1 : 3); q++)
+            if (has_nulls(ops[q]) || in.c[ops[q]].type != GSQL_T_FP64) return false;
+        RegSrc s;
+        s.kind = kind;
+        s.ua = slot_of(oa);
+        s.ub = kind ? slot_of(ob) : 0;
+        s.uc = kind == GSQL_EXPR_MUL_1MINUS_1PLUS ? slot_of(oc) : 0;
         int at = -1;
         for (int j = 0; j < L.nsrc; j++)
-            if (L.src[j].kind == s.kind && L.src[j].a == s.a && L.src[j].b == s.b && L.src[j].c == s.c) at = j;
+            if (L.src[j].kind == s.kind && L.src[j].ua == s.ua && L.src[j].ub == s.ub && L.src[j].uc == s.uc) at = j;
         if (at < 0) {
             if (L.nsrc == RG_MAX_SRC) return false;
             at = L.nsrc;
@@ -304,8 +400,37 @@ static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int 
         }
         L.agg_src[a] = at;
     }
-    if (L.nsrc == 0) {  // pure COUNT(*): still needs one (unused) source slot for the template
-        return false;
+    if (too_many || L.nsrc == 0) return false;  // (pure COUNT(*) shapes stay on the lane kernel)
+    int off = 0;  // 8-byte columns first: every region keeps its natural alignment
+    for (int pass = 0; pass < 2; pass++)
+        for (int u = 0; u < L.nused; u++)
+            if ((L.used_w[u] == 8) == (pass == 0)) {
+                L.used_off[u] = off;
+                off += RG_TILE * L.used_w[u];
+            }
+    L.tile_bytes = (off + 15) & ~15;
+    for (int j = 0; j < L.nsrc; j++) {
+        L.src[j].oa = L.used_off[L.src[j].ua];
+        L.src[j].ob = L.used_off[L.src[j].ub];
+        L.src[j].oc = L.used_off[L.src[j].uc];
+    }
+    for (int k = 0; k < nkeys; k++) {
+        L.key_off[k] = L.used_off[L.key_u[k]];
+        L.key_w[k] = L.used_w[L.key_u[k]];
+    }
+    if (L.rf_u >= 0) {  // every comparison with a constant is an interval test on integers
+        L.rf_off = L.used_off[L.rf_u];
+        L.rf_w = L.used_w[L.rf_u];
+        const int64_t v = spec.row_filter_value, mn = INT64_MIN, mx = INT64_MAX;
+        L.rf_lo = mn; L.rf_hi = mx; L.rf_neg = 0;
+        switch (spec.row_filter_op) {
+        case GSQL_CMP_LE: L.rf_hi = v; break;
+        case GSQL_CMP_LT: if (v == mn) { L.rf_lo = 1; L.rf_hi = 0; } else L.rf_hi = v - 1; break;
+        case GSQL_CMP_GE: L.rf_lo = v; break;
+        case GSQL_CMP_GT: if (v == mx) { L.rf_lo = 1; L.rf_hi = 0; } else L.rf_lo = v + 1; break;
+        case GSQL_CMP_EQ: L.rf_lo = L.rf_hi = v; break;
+        default: L.rf_lo = L.rf_hi = v; L.rf_neg = 1; break;
+        }
     }
     return true;
 }

@@ -208,16 +208,17 @@ __device__ __forceinline__ KeyVal gsql_load_key(const DCol &c, int64_t r, int ut
     k.is_null = c.nulls != nullptr && c.nulls[r] != 0;
     k.i = 0;
     if (k.is_null) return k;
+    // input columns are read once: evict-first loads keep the L2 for the hash-table slices (see ld_stream_* below)
     if (utype == GSQL_T_FP64) {
         double d;
-        if (c.type == GSQL_T_FP64) d = reinterpret_cast<const double *>(c.data)[r];
-        else if (c.type == GSQL_T_INT64) d = (double)reinterpret_cast<const int64_t *>(c.data)[r];
-        else d = (double)reinterpret_cast<const int32_t *>(c.data)[r];
+        if (c.type == GSQL_T_FP64) d = __ldcs(reinterpret_cast<const double *>(c.data) + r);
+        else if (c.type == GSQL_T_INT64) d = (double)__ldcs(reinterpret_cast<const long long *>(c.data) + r);
+        else d = (double)__ldcs(reinterpret_cast<const int *>(c.data) + r);
         k.i = __double_as_longlong(d);
     } else {
-        if (c.type == GSQL_T_INT32) k.i = reinterpret_cast<const int32_t *>(c.data)[r];
-        else if (c.type == GSQL_T_INT64) k.i = reinterpret_cast<const int64_t *>(c.data)[r];
-        else k.i = (int64_t)reinterpret_cast<const double *>(c.data)[r];
+        if (c.type == GSQL_T_INT32) k.i = __ldcs(reinterpret_cast<const int *>(c.data) + r);
+        else if (c.type == GSQL_T_INT64) k.i = __ldcs(reinterpret_cast<const long long *>(c.data) + r);
+        else k.i = (int64_t)__ldcs(reinterpret_cast<const double *>(c.data) + r);
     }
     return k;
 }
@@ -285,3 +286,8 @@ __device__ __forceinline__ unsigned long long ld_keep_8(const void *p, uint64_t 
 }
 
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// xchg.cu: reorders `rows` rows of up to 4 NULL-free device columns by destination = mulhi(fmix64(key), nparts) — the
+// table-slot range of the group-by / join tables — with the warp-synchronous split kernels of the push exchange
+// (nparts <= GSQL_MAX_RANKS).  out_data[c] receives column c; destinations are contiguous, in order.  Runs on ctx->stream.
+gsql_status local_split_by_slot_range(gsql_ctx *ctx, const DColSet &in, int key_col, int64_t rows, int nparts, void *const *out_data);

@@ -277,7 +277,7 @@ typedef struct gsql_expr_ins {
     union { int64_t i; double d; } k;
 } gsql_expr_ins;
 #define GSQL_MAX_EXPR_INS 24
-#define GSQL_MAX_EXPR_STACK 8
+#define GSQL_MAX_EXPR_STACK 4 /* operand stack depth: held in registers */
 #define GSQL_MAX_SCAN_OUT 16
 typedef struct gsql_expr {
     int32_t n;

@@ -639,20 +639,41 @@ def test_agg_reg_kernel_shapes_vs_oracle(gu, shape):
     gu.approx_rows_equal(got, exp, float_cols=fcols, key_cols=list(range(nk)), rtol=RTOL)
 
 
-def test_agg_partition_prepass_opt_in(gu, monkeypatch):
-    """High-cardinality group-by with the batch first reordered by table-slot range (k_agg_part_hist / _scatter)."""
-    monkeypatch.setenv("GSQL_AGG_PARTITION", "1")
+@pytest.mark.parametrize("shape", ["nullable_many_parts", "plain_int64_split_kernel", "plain_int32_split_kernel"])
+def test_agg_partition_prepass(gu, monkeypatch, shape):
+    """High-cardinality group-by with the batch first reordered by table-slot range: the scalar k_agg_part_hist / _scatter
+    (NULL masks, many partitions) and the warp-synchronous split kernels shared with the push exchange (one NULL-free
+    integer key, <= 16 partitions).  Thresholds are lowered so that test sizes take the pre-pass."""
+    from galaxysql_b200 import native as N
     monkeypatch.setenv("GSQL_AGG_PARTITION_MIN_ROWS", "1000")
-    monkeypatch.setenv("GSQL_AGG_PARTITION_BYTES", str(1 << 20))
     n = 600_000
-    k = (ku.rand_u64(n, 61) % np.uint64(200_000)).astype(np.int64) * 7919 - 5
     v = (ku.rand_u64(n, 62) % np.uint64(1000)).astype(np.float64)
-    w = (ku.rand_u64(n, 63) % np.uint64(1000)).astype(np.int32)
-    cols = [ku.with_nulls(k, 0.01, 64), ku.with_nulls(v, 0.02, 65), (w, None)]
-    aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_MAX, [2]), orc.AggCall(orc.AGG_AVG, [1])]
+    if shape == "nullable_many_parts":
+        monkeypatch.setenv("GSQL_AGG_PARTITION_BYTES", str(1 << 20))
+        k = (ku.rand_u64(n, 61) % np.uint64(200_000)).astype(np.int64) * 7919 - 5
+        w = (ku.rand_u64(n, 63) % np.uint64(1000)).astype(np.int32)
+        cols = [ku.with_nulls(k, 0.01, 64), ku.with_nulls(v, 0.02, 65), (w, None)]
+        aggs = [orc.AggCall(orc.AGG_COUNT_STAR), orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_MAX, [2]), orc.AggCall(orc.AGG_AVG, [1])]
+        fcols = [2, 4]
+    else:
+        monkeypatch.setenv("GSQL_AGG_PARTITION_BYTES", str(4 << 20))   # ~25 MB of table -> 7 partitions
+        if shape == "plain_int64_split_kernel":
+            k = (ku.rand_u64(n, 61) % np.uint64(200_000)).astype(np.int64) * 7919 - 5
+            k[:3] = np.int64(-(1 << 63))          # the table's empty-marker key travels through the split like any other
+        else:
+            k = (ku.rand_u64(n, 61) % np.uint64(200_000)).astype(np.int32) - 100_000
+        cols = [(k, None), (v, None)]
+        aggs = [orc.AggCall(orc.AGG_SUM, [1]), orc.AggCall(orc.AGG_COUNT_STAR)]
+        fcols = [1]
+    ctx = gu.ctx()
+    ctx.profile(True)
+    ctx.profile_reset()
     exp = orc.hash_agg(cols, [0], aggs, 300_000)
     got = gu.gpu_hash_agg(cols, [0], aggs, 300_000, mem="device", batches=2)
-    gu.approx_rows_equal(got, exp, float_cols=[2, 4], key_cols=[0], rtol=RTOL)
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    assert "agg_part_scatter" in prof and "agg_consume" in prof, prof
+    gu.approx_rows_equal(got, exp, float_cols=fcols, key_cols=[0], rtol=RTOL)
 
 
 @pytest.mark.parametrize("ngroups", [1, 6, 40])
