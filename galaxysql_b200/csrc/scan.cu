@@ -79,6 +79,9 @@ struct EStack4 {
     }
 };
 
+// NULLS = false: no input column of the batch carries a NULL buffer — every flag is a compile-time `false` and the flag
+// bookkeeping (byte permutes, selects) disappears from the instruction stream.
+template <bool NULLS>
 __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, int64_t base, const bool (&live)[SC_RPT], long long (&out)[SC_RPT],
                                            bool (&outnull)[SC_RPT]) {
     EStack4 S;
@@ -98,7 +101,7 @@ __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, in
 #pragma unroll
             for (int k = 0; k < SC_RPT; k++) {
                 const int64_t r = live[k] ? base + (int64_t)k * SC_THREADS : base;
-                const bool n = c.nulls != nullptr && c.nulls[r] != 0;
+                const bool n = NULLS && c.nulls != nullptr && c.nulls[r] != 0;
                 long long v = is32 ? (long long)ld_stream_4(reinterpret_cast<const int *>(c.data) + r) : ld_stream_8(reinterpret_cast<const long long *>(c.data) + r);
                 S.v0[k] = n ? 0 : v;
                 S.n0[k] = n;
@@ -122,7 +125,7 @@ __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, in
             break;
         case GSQL_OP_IS_NULL:
 #pragma unroll
-            for (int k = 0; k < SC_RPT; k++) { S.v0[k] = S.n0[k] ? 1 : 0; S.n0[k] = false; }
+            for (int k = 0; k < SC_RPT; k++) { S.v0[k] = (NULLS && S.n0[k]) ? 1 : 0; S.n0[k] = false; }
             break;
         case GSQL_OP_CAST_F64:
             if (!I.af) {
@@ -142,7 +145,7 @@ __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, in
 #pragma unroll
             for (int k = 0; k < SC_RPT; k++) {
                 const long long b = S.v0[k], a = S.v1[k];
-                const bool bn = S.n0[k], an = S.n1[k];
+                const bool bn = NULLS && S.n0[k], an = NULLS && S.n1[k];
                 if (is_and) {
                     const bool f = (!an && a == 0) || (!bn && b == 0);
                     S.v1[k] = f ? 0 : 1;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, in
 #pragma unroll
             for (int k = 0; k < SC_RPT; k++) {
                 const long long b = S.v0[k], a = S.v1[k];
-                const bool n = S.n0[k] || S.n1[k];
+                const bool n = NULLS && (S.n0[k] || S.n1[k]);
                 long long res = 0;
                 if (fl) {
                     const double x = as_f(a, I.af), y = as_f(b, I.bf);
@@ -199,9 +202,10 @@ __device__ __forceinline__ void eval_expr4(const DExpr &E, const DColSet &in, in
         }
     }
 #pragma unroll
-    for (int k = 0; k < SC_RPT; k++) { out[k] = S.v0[k]; outnull[k] = S.n0[k]; }
+    for (int k = 0; k < SC_RPT; k++) { out[k] = S.v0[k]; outnull[k] = NULLS && S.n0[k]; }
 }
 
+template <bool NULLS>
 __global__ void __launch_bounds__(SC_THREADS) k_scan(const ScanDev *__restrict__ S, const __grid_constant__ DColSet in, int64_t rows,
                                                      const __grid_constant__ ScanOut O, unsigned long long *cursor, int32_t *flags) {
     __shared__ unsigned int wcount[SC_THREADS / 32][SC_RPT];
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan(const ScanDev *__restrict__
         if (S->has_filter) {
             long long fv[SC_RPT];
             bool fn[SC_RPT];
-            eval_expr4(S->filter, in, safe, pass, fv, fn);
+            eval_expr4<NULLS>(S->filter, in, safe, pass, fv, fn);
 #pragma unroll
             for (int k = 0; k < SC_RPT; k++) pass[k] = pass[k] && !fn[k] && fv[k] != 0;
         }
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(SC_THREADS) k_scan(const ScanDev *__restrict__
         for (int e = 0; e < S->n_out; e++) {
             long long v[SC_RPT];
             bool n[SC_RPT];
-            eval_expr4(S->out[e], in, safe, pass, v, n);
+            eval_expr4<NULLS>(S->out[e], in, safe, pass, v, n);
             const bool is32 = S->out[e].out_type == GSQL_T_INT32;
 #pragma unroll
             for (int k = 0; k < SC_RPT; k++) {
@@ -430,8 +434,14 @@ extern "C" gsql_status gsql_scan_apply(gsql_scan *s, const gsql_batch *in, gsql_
         KernelScope ks(ctx, "scan_filter_project");
         int64_t tiles = div_up(in->rows, SC_TILE);
         int64_t g = tiles < (int64_t)ctx->sm_count * 8 ? tiles : (int64_t)ctx->sm_count * 8;
-        k_scan<<<(int)g, SC_THREADS, 0, ctx->stream>>>(reinterpret_cast<const ScanDev *>(s->dev.p), cols, in->rows, O, s->cursor.as<unsigned long long>(),
-                                                       s->flags.as<int32_t>());
+        bool any_mask = false;
+        for (int i = 0; i < sb.ncols; i++) any_mask |= sb.cols[i].nulls != nullptr;
+        if (any_mask)
+            k_scan<true><<<(int)g, SC_THREADS, 0, ctx->stream>>>(reinterpret_cast<const ScanDev *>(s->dev.p), cols, in->rows, O, s->cursor.as<unsigned long long>(),
+                                                                 s->flags.as<int32_t>());
+        else
+            k_scan<false><<<(int)g, SC_THREADS, 0, ctx->stream>>>(reinterpret_cast<const ScanDev *>(s->dev.p), cols, in->rows, O, s->cursor.as<unsigned long long>(),
+                                                                  s->flags.as<int32_t>());
     }
     GSQL_CUDA(ctx, cudaGetLastError());
     struct { unsigned long long n; unsigned long long pad; } h;

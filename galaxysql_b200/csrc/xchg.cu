@@ -825,9 +825,8 @@ constexpr int PW_TILE = 32 * PW_RPL;      // 256 rows per warp tile
 constexpr int PW_WARPS = 4;               // 128 threads per block: <= 32 KB of staging, five blocks per SM
 
 template <bool FAST, int NC>
-__global__ void __launch_bounds__(PW_WARPS * 32, 5) k_xchg_push_w(const __grid_constant__ PushParams P) {
+__global__ void __launch_bounds__(PW_WARPS * 32, 8) k_xchg_push_w(const __grid_constant__ PushParams P) {
     __shared__ __align__(16) unsigned long long wstage[PW_WARPS][NC][PW_TILE];  // a warp's tile, column-major, in destination order
-    __shared__ unsigned char wdest[PW_WARPS][PW_TILE];
     __shared__ unsigned int wcnt[PW_WARPS][GSQL_MAX_RANKS];
     __shared__ unsigned int wgo[PW_WARPS][GSQL_MAX_RANKS + 1];
     __shared__ unsigned long long wg[PW_WARPS][GSQL_MAX_RANKS];
@@ -841,28 +840,16 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 5) k_xchg_push_w(const __grid_c
     const int64_t r1 = r0 + P.X.chunk < P.X.rows ? r0 + P.X.chunk : P.X.rows;
     for (int64_t t0 = r0 + (int64_t)warp * PW_TILE; t0 < r1; t0 += (int64_t)PW_WARPS * PW_TILE) {
         const int n_tile = (int)(r1 - t0 < PW_TILE ? r1 - t0 : PW_TILE);
+        // ---- 1. destinations (the key loads of all eight rows are in flight together)
         int d[PW_RPL];
-        unsigned long long val[NC][PW_RPL];
 #pragma unroll
         for (int k = 0; k < PW_RPL; k++) {
             const int64_t r = t0 + k * 32 + lane;
             d[k] = r < r1 ? push_dest<FAST>(P.X, r) : -1;
         }
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const DCol &col = P.X.in.c[c];
-            const bool is32 = col.type == GSQL_T_INT32;
-#pragma unroll
-            for (int k = 0; k < PW_RPL; k++) {
-                const int64_t r = t0 + k * 32 + lane;
-                val[c][k] = 0;
-                if (r < r1) val[c][k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
-                                             : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
-            }
-        }
         if (lane < GSQL_MAX_RANKS) wcnt[warp][lane] = 0;
         __syncwarp();
-        // offset of every row inside its destination's part of the warp tile
+        // ---- 2. offset of every row inside its destination's part of the warp tile
         unsigned int off[PW_RPL];
 #pragma unroll
         for (int k = 0; k < PW_RPL; k++) {
@@ -894,25 +881,41 @@ __global__ void __launch_bounds__(PW_WARPS * 32, 5) k_xchg_push_w(const __grid_c
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < PW_RPL; k++) {
-            if (d[k] < 0) continue;
-            const unsigned int pos = wgo[warp][d[k]] + off[k];
-            wdest[warp][pos] = (unsigned char)d[k];
-#pragma unroll
-            for (int c = 0; c < NC; c++) wstage[warp][c][pos] = val[c][k];
-        }
-        __syncwarp();
+        for (int k = 0; k < PW_RPL; k++) off[k] += d[k] >= 0 ? wgo[warp][d[k]] : 0u;  // position in the staged tile
+        // ---- 3. column after column: eight loads in flight per lane, staged in destination order
 #pragma unroll
         for (int c = 0; c < NC; c++) {
-            const bool is32 = P.X.in.c[c].type == GSQL_T_INT32;
+            const DCol &col = P.X.in.c[c];
+            const bool is32 = col.type == GSQL_T_INT32;
+            unsigned long long v[PW_RPL];
 #pragma unroll
             for (int k = 0; k < PW_RPL; k++) {
-                const int i = k * 32 + lane;
-                if (i < n_tile) {
-                    const int dd = wdest[warp][i];
-                    const unsigned long long row = wg[warp][dd] + (unsigned)(i - (int)wgo[warp][dd]);
-                    if (is32) reinterpret_cast<int *>(P.peer_base[dd] + P.col_off[c])[row] = (int)(unsigned)wstage[warp][c][i];
-                    else reinterpret_cast<long long *>(P.peer_base[dd] + P.col_off[c])[row] = (long long)wstage[warp][c][i];
+                const int64_t r = t0 + k * 32 + lane;
+                v[k] = 0;
+                if (d[k] >= 0) v[k] = is32 ? (unsigned long long)(unsigned)ld_stream_4(reinterpret_cast<const int *>(col.data) + r)
+                                           : (unsigned long long)ld_stream_8(reinterpret_cast<const long long *>(col.data) + r);
+            }
+#pragma unroll
+            for (int k = 0; k < PW_RPL; k++)
+                if (d[k] >= 0) wstage[warp][c][off[k]] = v[k];
+        }
+        __syncwarp();
+        // ---- 4. flush: staged position i belongs to the destination whose range [wgo[dd], wgo[dd+1]) holds it; its row in
+        //         that GPU's receive buffer is computed once and used for every column
+#pragma unroll
+        for (int k = 0; k < PW_RPL; k++) {
+            const int i = k * 32 + lane;
+            if (i < n_tile) {
+                int dd = 0;
+#pragma unroll
+                for (int q = 1; q < GSQL_MAX_RANKS; q++)
+                    if (q < R && (unsigned)i >= wgo[warp][q]) dd = q;
+                const unsigned long long row = wg[warp][dd] + (unsigned)(i - (int)wgo[warp][dd]);
+                char *base = P.peer_base[dd];
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    if (P.X.in.c[c].type == GSQL_T_INT32) reinterpret_cast<int *>(base + P.col_off[c])[row] = (int)(unsigned)wstage[warp][c][i];
+                    else reinterpret_cast<long long *>(base + P.col_off[c])[row] = (long long)wstage[warp][c][i];
                 }
             }
         }
@@ -1067,7 +1070,7 @@ static void fill_peers(gsql_xchg *x, PeerSet *S) {
 }
 
 static int push_blocks(gsql_ctx *ctx, int64_t rows) {
-    int per_sm = 5;
+    int per_sm = 8;
     if (const char *e = getenv("GSQL_XCHG_PUSH_CTAS_PER_SM")) per_sm = atoi(e);
     if (per_sm < 1) per_sm = 1;
     int64_t nb = (int64_t)ctx->sm_count * per_sm;

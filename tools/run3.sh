@@ -1,7 +1,7 @@
 set -x
 cd $GRAFT_REPO_ROOT
-timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_pipelines_gpu.py -m gpu -x -q -k "agg or scan or q3 or two_phase" 2>&1 | tail -8
-timeout 300 python tools/pushbench.py 2>&1 | tail -4
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_pipelines_gpu.py tests/test_multigpu.py -m gpu -x -q -k "agg or scan or q3 or two_phase or push or across" 2>&1 | tail -8
+timeout 300 python tools/pushbench.py 2>&1 | tail -3
 timeout 900 python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; python - <<PY
 import json
 d=json.loads(open("gpurun_out/bench_n1.json").read().strip().splitlines()[-1])
