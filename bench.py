@@ -33,6 +33,11 @@ BUILD_ALG_BYTES = 24  # 16 row read + 8 table write
 METRIC = "joined+aggregated rows/sec; achieved HBM GB/s vs peak, at 1/2/4/8 B200"
 
 
+def c2_workload_name(world: int) -> str:
+    base = "C2: inner hash join 100M build x 1B probe, BIGINT key + 2 INT payloads"
+    return base + (", 1 GPU" if world == 1 else f" per GPU, both sides hash-shuffled across {world} GPUs (partition-and-push over NVLink)")
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -43,12 +48,12 @@ def parse_args():
                     help="fraction of config 2 (testing only; the contract value is 1.0)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-aux", action="store_true", help="skip the auxiliary group-by measurement (Q1 shape)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the group-by rooflines (C1 / C3 / C5 share) and the Q3 / C5 pipeline entries")
     ap.add_argument("--e2e-batch", type=int, default=125_000_000, help="probe rows per host batch in the e2e leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "q3", "c5"],
                     help="c2 (default, the contract line): BASELINE config 2 join; q3 / c5: BASELINE configs 4 / 5 pipelines")
-    ap.add_argument("--slabs", type=int, default=int(os.environ.get("GSQL_BENCH_SLABS", "4")),
-                    help="probe-side slabs of the shuffled join (N > 1): slab k is probed while slab k+1 crosses NVLink")
+    ap.add_argument("--slabs", type=int, default=int(os.environ.get("GSQL_BENCH_SLABS", "1")),
+                    help="slabs of the pushed side (N > 1): slab k is consumed while slab k+1 crosses NVLink; 1 measured best at N = 2..8 (r02)")
     return ap.parse_args()
 
 
@@ -163,6 +168,38 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process (and the pinned buffers it allocates from now on: first touch) to the NUMA node of GPU `index`:
+    at N = 8 the r01 end-to-end leg delivered 2.3x one rank's host throughput because ranks copied across sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        import torch
+        uuid = str(torch.cuda.get_device_properties(index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:   # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:120]}
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -178,7 +215,7 @@ def host_threads() -> int:
     return max(1, min(os.cpu_count() or 1, 16))  # ExecUtils.getParallelismForLocal: min(cores, 16)
 
 
-CPU_SAMPLE = (25_000_000, 100_000_000)  # 1/4 of the build side (DRAM-resident table, like the full size), 1/10 of the probe
+CPU_SAMPLE = (100_000_000, 100_000_000)  # the FULL 100 M-row build side (table size is what the probe's cache misses depend on), 1/10 of the probe rows
 _cpu_tables = {}
 
 
@@ -218,12 +255,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int64", "data": "synthetic",
-        "config": {"workload": "C2: inner hash join 100M build x 1B probe, BIGINT key + 2 INT payloads" + (", 1 GPU" if args.gpus == 1 else f" per GPU x {args.gpus}"),
-                   "sample_build_rows": sb, "sample_probe_rows": sp,
-                   "note": "bounded sample of the workload per step on the host cores; the reference Java cannot run (no JDK in the "
-                           "image) so this is the oracle port in the reference's parallel shape (P drivers, 1000-row chunks, shared CAS table)"},
+        "config": {"workload": c2_workload_name(args.gpus), "build_rows_per_gpu": C2_BUILD, "probe_rows_per_gpu": C2_PROBE, "scale": 1.0},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": host_threads(), "kind": "port",
-                         "sample": f"{sb} build x {sp} probe rows per step, {host_threads()} threads, 1000-row chunks"},
+                         "sample": f"{sb} build x {sp} probe rows per step (the full build side; 1/10 of the probe rows), {host_threads()} threads, "
+                                   "1000-row chunks; the reference Java cannot run (no JDK in the image): this is the oracle port in the reference's "
+                                   "parallel shape (P = min(cores, 16) drivers, shared CAS chained table)"},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -244,6 +280,7 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         # the AllToAllv is a grouped ncclSend/ncclRecv per peer: give the p2p path all the channels NVLink can use
         os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
@@ -389,7 +426,7 @@ def run_ours(args):
     # ---- e2e: host (pinned) buffers through the C-ABI, rank-local, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev)
+        e2e = run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev, numa)
     # free the big device tables before the CPU leg
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -400,23 +437,33 @@ def run_ours(args):
                          f"(build {d['build_s']:.2f}s + probe {d['probe_s']:.2f}s)"}
     # ---- auxiliary (N = 1 only): the group-by half of the metric on its BASELINE shape, device-resident like `value`.
     # Never allowed to take the headline down: any failure is reported inside the key.
-    aux = None
-    if rank == 0 and world == 1 and not args.no_aux:
-        del out_cols, probe, build    # ~50 GB back before the aggregation tables are generated
+    if not args.no_aux:
+        # ---- the rest of the metric inside the same line (the driver keeps `roofline`): the group-by rooflines (N = 1) and
+        # the two pipelines BASELINE.json names for 8 GPUs — TPC-H Q3 and the high-cardinality GROUP BY — at this N
+        if world > 1:
+            sj.close()
+        del out_cols, probe, build    # ~50 GB back before the other tables are generated
         torch.cuda.empty_cache()
-        for key, fn in (("agg_q1", run_aux_agg), ("agg_c5", run_aux_agg_c5), ("agg_c1", run_aux_agg_c1)):
-            try:
-                roofline[key] = fn(ctx, api, N, synth, dev, args.scale, peak)
-            except Exception as e:  # noqa: BLE001
-                roofline[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if rank == 0 and world == 1:
+            for key, fn in (("agg_q1", run_aux_agg), ("agg_c5", run_aux_agg_c5), ("agg_c1", run_aux_agg_c1)):
+                try:
+                    roofline[key] = fn(ctx, api, N, synth, dev, args.scale, peak)
+                except Exception as e:  # noqa: BLE001
+                    roofline[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
+        for wl in ("q3", "c5"):
+            m = measure_pipeline(args, wl, 3, 2, ctx, stream, world, rank, local_rank, dev)   # collective: every rank takes part
+            roofline["pipeline_" + wl] = {"workload": m["config"]["workload"], "rows_per_s": m["value"], "ms_per_step": m["ms_per_step"],
+                                          "n_gpus": world, "parity": m["parity"], "stats": m["stats"],
+                                          "per_kernel_ms_per_step": m["roofline"]["per_kernel_ms_per_step"]}
+            torch.cuda.empty_cache()
     if rank == 0:
         info = state["info"]
         line = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
             "data": "synthetic",
-            "config": {"workload": "C2: inner hash join 100M build x 1B probe, BIGINT key + 2 INT payloads" +
-                                   (f" per GPU, hash-shuffled across {world} GPUs (AllToAllv)" if world > 1 else ", 1 GPU"),
+            "config": {"workload": c2_workload_name(world),
                        "build_rows_per_gpu": nb, "probe_rows_per_gpu": npr, "scale": args.scale,
                        "l2": "inputs (16 GB probe per step) are far larger than the 126 MB L2; no explicit flush",
                        "step": "build (consume + finish) + probe of the full probe table" + (" after the key shuffle" if world > 1 else ""),
@@ -562,7 +609,13 @@ def run_aux_agg_c1(ctx, api, N, synth, dev, scale, peak_gbs):
 
 # ------------------------------------------------------------------------------------------------ q3 / c5 pipelines
 def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
-    """--workload q3: BASELINE config 4 (TPC-H Q3, SF300 over 8 GPUs = SF37.5 per GPU, weak scaling);
+    line = measure_pipeline(args, args.workload, args.steps, args.warmup, ctx, stream, world, rank, local_rank, dev, with_clocks=True)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def measure_pipeline(args, workload, steps, warmup, ctx, stream, world, rank, local_rank, dev, with_clocks=False):
+    """workload q3: BASELINE config 4 (TPC-H Q3, SF300 over 8 GPUs = SF37.5 per GPU, weak scaling);
     --workload c5: BASELINE config 5 (GROUP BY k, SUM(double): 500 M rows and 6.25 M keys per GPU).  One step = the whole
     pipeline of galaxysql_b200/pipelines.py over device-resident tables; value = input rows of all ranks / max step time."""
     import torch
@@ -570,7 +623,7 @@ def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
     from galaxysql_b200 import api, native as N, pipelines, synth
     sc = args.scale
     peak, peak_src = measured_peak_gbs()
-    if args.workload == "q3":
+    if workload == "q3":
         ncust, nord, nline = int(5_625_000 * sc), int(56_250_000 * sc), int(225_000_000 * sc)
         g = torch.Generator(device=dev)
         g.manual_seed(1000 + rank)
@@ -617,9 +670,9 @@ def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and with_clocks:
         sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     barrier()
     ctx.profile(True)
@@ -629,7 +682,7 @@ def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
     barrier()
     t0 = time.time()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     ev1.record(stream)
     barrier()
@@ -638,15 +691,15 @@ def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
     prof = ctx.profile_dump()
     ctx.profile(False)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.stop(t0, t1) if rank == 0 and with_clocks else None
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = ms_total / steps
     # ---- parity of the last step's result against a torch restatement of the query on the same tables (outside the timed region)
     out = state["out"]
-    if args.workload == "q3":
+    if workload == "q3":
         def allgather(t):
             if world == 1:
                 return t
@@ -692,20 +745,18 @@ def run_pipeline_workload(args, ctx, stream, world, rank, local_rank, dev):
                   "groups": int(got[2]), "what": "sum of SUM(v) and of COUNT(*) over all groups vs the column totals; groups <= distinct keys"}
         stats = {"mode": agg.mode}
     assert parity["match"], parity
-    if rank == 0:
-        value = rows_in * world / (ms_step / 1e3)
-        alg = None
-        line_ = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                 "dtype": "f64" if args.workload == "c5" else "int64+f64", "data": "synthetic",
-                 "config": {"workload": what, "slabs": args.slabs, "scale": sc, "l2": "tables are far larger than the 126 MB L2; no explicit flush"},
-                 "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-                              "per_kernel_ms_per_step": {k_: v_[1] / args.steps for k_, v_ in sorted(prof.items())}, "peak_source": peak_src},
-                 "parity": parity, "stats": stats, "clocks": clocks, "gpu_launches": int(launches)}
-        print(json.dumps(line_), flush=True)
+    (q3 if workload == "q3" else agg).close()
+    value = rows_in * world / (ms_step / 1e3)
+    return {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if workload == "c5" else "int64+f64", "data": "synthetic",
+            "config": {"workload": what, "slabs": args.slabs, "scale": sc, "l2": "tables are far larger than the 126 MB L2; no explicit flush"},
+            "roofline": {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+                         "per_kernel_ms_per_step": {k_: v_[1] / steps for k_, v_ in sorted(prof.items())}, "peak_source": peak_src},
+            "parity": parity, "stats": stats, "clocks": clocks, "gpu_launches": int(launches)}
 
 
-def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
+def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev, numa=None):
     """The join as a host caller drives it: pinned host Blocks in, pinned host Blocks out, every copy timed."""
     import torch
     import torch.distributed as dist
@@ -718,7 +769,7 @@ def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
     try:
         hbuild = [torch.empty(nb, dtype=c.dtype, pin_memory=True) for c in build]
         hprobe = [torch.empty(npr, dtype=c.dtype, pin_memory=True) for c in probe]
-        hout = [torch.empty(batch, dtype=tt[t], pin_memory=True) for t in types + types]
+        hout = [torch.empty(batch if world == 1 else 1, dtype=tt[t], pin_memory=True) for t in types + types]
     except RuntimeError:
         ok = 0
     if world > 1:
@@ -732,14 +783,16 @@ def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
     for h, c in zip(hbuild, build):
         h.copy_(c)
     for i, (h, c) in enumerate(zip(hprobe, probe)):
-        if i == 0 and world > 1:  # rank-local leg: map every probe key into this rank's share of the key space
-            h.copy_((c // world) * world + rank)
-        else:
-            h.copy_(c)
+        h.copy_(c)
     torch.cuda.synchronize()
 
     def view(tensors, lo, hi):
         return [(t[lo:hi].numpy(), None) for t in tensors]
+
+    if world > 1:
+        # N > 1: the same work as `value` — upload the rank's shards from pinned host memory, shuffle both sides over NVLink,
+        # join, download the joined rows into pinned host memory — every copy inside the timed region
+        return run_e2e_multi(args, ctx, api, N, hbuild, hprobe, nb, npr, world, rank, dev, numa, build, probe)
 
     def step():
         j = api.HashJoin(ctx, N.JOIN_INNER, types, types, [0], [0], expected_build_rows=nb)
@@ -769,10 +822,70 @@ def run_e2e(args, ctx, api, N, build, probe, nb, npr, world, rank, dev):
     assert total == npr
     h2d = nb * 16 + npr * 16
     d2h = npr * 32
-    return {"value": npr * world / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+    return {"value": npr * world / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "numa_binding": numa,
             "ms_per_step": dt * 1000.0, "steps": steps, "probe_batch_rows": batch,
             "path": "gsql_join_build_consume/gsql_join_probe with GSQL_MEM_HOST pinned batches" +
                     (" (every rank joins its own 100M x 1B shard from host memory; probe keys remapped to the rank's key share)" if world > 1 else "")}
+
+
+def run_e2e_multi(args, ctx, api, N, hbuild, hprobe, nb, npr, world, rank, dev, numa, dbuild, dprobe):
+    import torch
+    import torch.distributed as dist
+    from galaxysql_b200 import pipelines
+    types = [N.T_INT64, N.T_INT32, N.T_INT32]
+    tt = {N.T_INT64: torch.int64, N.T_INT32: torch.int32}
+    cap = int(npr * 1.02) + 1_000_000
+    ok, hout = 1, None
+    try:
+        hq = cap // 4 + 1   # the joined rows leave through a quarter-size pinned buffer, four times (bounds pinned host memory per rank)
+        hout = [torch.empty(hq, dtype=tt[t], pin_memory=True) for t in types + types]
+    except RuntimeError:
+        ok = 0
+    okt = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+    if not int(okt.item()):
+        return {"value": None, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "error": "pinned host output buffers could not be allocated on every rank"}
+    out_cols = [(torch.empty(cap, dtype=tt[t], device=dev), None) for t in types + types]
+    sj = pipelines.ShuffledJoin(ctx, N.JOIN_INNER, types, types, [0], [0], build_capacity=int(nb * 1.05) + 1_000_000, probe_capacity=cap, nslabs=args.slabs)
+    st = ctx.torch_stream()
+
+    def step():
+        with torch.cuda.stream(st):
+            for h, d in zip(hbuild, dbuild):
+                d.copy_(h, non_blocking=True)
+            for h, d in zip(hprobe, dprobe):
+                d.copy_(h, non_blocking=True)
+        sj.run([(c, None) for c in dprobe], [(c, None) for c in dbuild], out_cols=out_cols, out_capacity=cap)
+        n = sj.last_rows
+        with torch.cuda.stream(st):
+            for lo in range(0, n, hq):
+                m = min(hq, n - lo)
+                for h, (d, _) in zip(hout, out_cols):
+                    h[:m].copy_(d[lo:lo + m], non_blocking=True)
+        st.synchronize()
+        return n
+
+    steps = max(1, min(args.steps, 3))
+    step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        n = step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    rows = torch.tensor([n], dtype=torch.int64, device=dev)
+    dist.all_reduce(rows)
+    assert int(rows.item()) == npr * world
+    sj.close()
+    return {"value": npr * world / dt, "unit": "rows/s", "h2d_bytes_per_step": nb * 16 + npr * 16, "d2h_bytes_per_step": int(n) * 32,
+            "ms_per_step": dt * 1000.0, "steps": steps, "numa_binding": numa,
+            "path": "pinned host shards -> H2D -> gsql_xchg_push of both sides -> gsql_join_* on the receive buffers -> D2H of the joined rows; "
+                    "per-rank bytes; copies are not overlapped with the kernels"}
 
 
 def main():

@@ -675,6 +675,45 @@ def plan_layout(nranks: int, nslabs: int, me: int, matrix):
     return send, recv, rows, int(worst)
 
 
+def serde_serialize(ctx: Context, cols, page_rows: int = 1024):
+    """Chunk columns -> the reference's MPP wire bytes (gsql_serde_serialize): numpy uint8 for host columns, a CUDA uint8
+    tensor for device columns."""
+    bv = _BatchView(cols)
+    need = C.c_int64()
+    ctx.check(ctx.lib.gsql_serde_size(ctx.ptr, bv.ref(), page_rows, C.byref(need)))
+    n = need.value
+    if bv.mem == N.MEM_DEVICE:
+        out = torch.empty(max(n, 1), dtype=torch.uint8, device=f"cuda:{ctx.device}")
+        ptr = out.data_ptr()
+    else:
+        out = np.empty(max(n, 1), dtype=np.uint8)
+        ptr = out.ctypes.data
+    got = C.c_int64()
+    ctx.check(ctx.lib.gsql_serde_serialize(ctx.ptr, bv.ref(), page_rows, C.c_void_p(ptr), n, C.byref(got)))
+    assert got.value == n
+    return out[:n]
+
+
+def serde_deserialize(ctx: Context, data, types: Sequence[int]):
+    """Wire bytes (numpy uint8 / bytes, or a CUDA uint8 tensor) -> [(values, nulls)] in the same memory space."""
+    if _is_tensor(data):
+        mem, ptr, nbytes = N.MEM_DEVICE, data.data_ptr(), data.numel()
+    else:
+        data = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else np.ascontiguousarray(data, dtype=np.uint8)
+        mem, ptr, nbytes = N.MEM_HOST, data.ctypes.data, data.size
+    cap = 0
+    while True:
+        out = _alloc_out(ctx, types, max(cap, 1), mem, [True] * len(types))
+        ob, _keep = _out_batch(out, types, 0, mem)
+        n = C.c_int64()
+        st = ctx.lib.gsql_serde_deserialize(ctx.ptr, C.c_void_p(ptr), nbytes, mem, C.byref(ob), cap, C.byref(n))
+        if st == N.E_CAPACITY:
+            cap = n.value
+            continue
+        ctx.check(st)
+        return _trim(out, n.value)
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     st = N.load().gsql_comm_unique_id(buf)

@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "_build")
 SO = os.path.join(OUT, "libgsql_gpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["ctx.cu", "join.cu", "agg.cu", "xchg.cu", "scan.cu"]
+SOURCES = ["ctx.cu", "join.cu", "agg.cu", "xchg.cu", "scan.cu", "serde.cu"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -129,7 +129,10 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
     if (!dedicated) s = __umul64hi(gsql_fmix64(d), P.nslots);
     while (true) {
         ASlot *sl = &P.slots[s];
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(&sl->digest);
+        // first look through the read-only path with an evict_last hint (the partition's slice of the table stays in L2 under the
+        // evict-first input stream).  A stale EMPTY is harmless: the CAS below returns the real content; a digest never changes
+        // once written, so a stale non-EMPTY value cannot exist.
+        unsigned long long cur = ld_keep_8(&sl->digest, l2_policy_evict_last());
         bool mine = false;
         if (dedicated) {
             // dedicated slots are claimed through gid only: digest field carries a "claimed" mark
@@ -241,7 +244,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     }
     switch (a.kind) {
     case GSQL_AGG_COUNT_STAR:
-        atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
+        red_add_u64_keep(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL, l2_policy_evict_last());
         return;
     case GSQL_AGG_COUNT:
         for (int i = 0; i < a.ncols; i++)
@@ -255,7 +258,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     switch (a.kind) {
     case GSQL_AGG_SUM:
         if (a.in_type == GSQL_T_FP64) {
-            atomicAdd(&a.d[gid], val_f64(P, c, r));
+            red_add_f64_keep(&a.d[gid], val_f64(P, c, r), l2_policy_evict_last());
         } else {  // exact 128-bit: lo += v (carry out), hi += sign extension + carry
             long long v = val_i64(P, c, r);
             unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)v);
@@ -263,12 +266,12 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
             long long carry = (sum < old ? 1 : 0) + (v < 0 ? -1 : 0);
             if (carry) atomicAdd(reinterpret_cast<unsigned long long *>(&a.hi[gid]), (unsigned long long)carry);
         }
-        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_AVG:
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
-        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_SUM0:
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, c, r));
@@ -276,7 +279,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     case GSQL_AGG_AVG_MERGE:  // (partial sum, partial count): the sum is NULL exactly when its count is 0
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         if (!val_null(P, a.cols[1], r)) atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, a.cols[1], r));
-        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     case GSQL_AGG_MIN:
     case GSQL_AGG_MAX: {
@@ -284,7 +287,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
         long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(val_f64(P, c, r), mx) : val_i64(P, c, r);
         if (mx) atomicMax(reinterpret_cast<long long *>(&a.l[gid]), v);
         else atomicMin(reinterpret_cast<long long *>(&a.l[gid]), v);
-        if (!a.has[gid]) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
         return;
     }
     default: return;

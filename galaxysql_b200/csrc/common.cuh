@@ -285,6 +285,20 @@ __device__ __forceinline__ unsigned long long ld_keep_8(const void *p, uint64_t 
     return v;
 }
 
+// fp64 / u64 reductions that keep their line in L2 with evict_last priority (group-by accumulators: a partition's slice of
+// them is re-touched for millions of rows while the input streams by with evict-first loads)
+__device__ __forceinline__ void red_add_f64_keep(double *p, double v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void red_add_u64_keep(unsigned long long *p, unsigned long long v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_keep_u8(const uint8_t *p, uint64_t pol) {
+    unsigned int v;
+    asm volatile("ld.global.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
 static inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // xchg.cu: reorders `rows` rows of up to 4 NULL-free device columns by destination = mulhi(fmix64(key), nparts) — the

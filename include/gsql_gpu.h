@@ -370,6 +370,26 @@ int64_t gsql_xchg_plan_layout(int32_t nranks, int32_t nslabs, int32_t me, const 
                               int64_t *recv_base, int64_t *slab_rows);
 void gsql_xchg_destroy(gsql_xchg *x);
 
+/* ------------------------------------------------------------------------------------------------ wire codec */
+/* The MPP wire format of a Chunk (mpp/execution/buffer/PagesSerde.java:57-115 uncompressed path,
+ * PagesSerdeUtil.java:36-58 writeRawPage / readRawPage, :50-58 + :60-67 the SerializedChunk framing,
+ * chunk/{Integer,Long,Double}BlockEncoding.java + EncoderUtil.java:43-150), so that a GPU task can exchange pages with
+ * stock Java tasks on other nodes.  All integers little-endian (airlift Slice).  A batch becomes consecutive pages of
+ * `page_rows` rows:
+ *     page   := int32 positionCount | int8 marker (0 = UNCOMPRESSED) | int32 uncompressedSize | int32 sizeInBytes | raw
+ *     raw    := int32 blockCount | block*
+ *     block  := int32 positionCount | nullbits (ceil(n/8) bytes, first row = most significant bit) | non-NULL values in row order
+ * Compression (the optional LZ4 step of PagesSerde) is not produced; compressed pages are rejected by deserialize. */
+/* Serialized size of `in` cut into pages of page_rows rows (exact; needs one pass over the NULL masks). */
+gsql_status gsql_serde_size(gsql_ctx *ctx, const gsql_batch *in, int32_t page_rows, int64_t *bytes);
+/* `out_bytes` lives in in->mem.  GSQL_E_CAPACITY with *bytes = the need when capacity is too small. */
+gsql_status gsql_serde_serialize(gsql_ctx *ctx, const gsql_batch *in, int32_t page_rows, void *out_bytes, int64_t capacity, int64_t *bytes);
+/* Decodes every page of `bytes` (host or device, `mem`) into `out` (same mem; out->ncols columns of `types`, each with a
+ * nulls buffer, capacity out_capacity rows).  GSQL_E_CAPACITY with *out_rows = the need; GSQL_E_INVALID on a malformed or
+ * compressed page. */
+gsql_status gsql_serde_deserialize(gsql_ctx *ctx, const void *bytes, int64_t nbytes, int32_t mem, gsql_batch *out, int64_t out_capacity,
+                                   int64_t *out_rows);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -203,3 +203,21 @@ def test_mt_baseline_matches_single_thread():
     k = (ku.rand_u64(n_out, 23) % np.uint64(4096)).astype(np.int32)
     r = orc.mt_hash_agg([(k, None)], [0], [orc.AggCall(orc.AGG_COUNT_STAR)], 1024, nthreads=4)
     assert r["groups"] == len(np.unique(k))
+
+
+def test_wire_format_restatement_round_trip_and_layout():
+    """oracle/serde.py: known-answer bytes of a tiny page worked out by hand from PagesSerdeUtil / LongBlockEncoding /
+    EncoderUtil (frame 13 bytes, blockCount, positionCount, bit stream MSB-first, non-NULL values only) and a round trip."""
+    import struct
+    from oracle import serde
+    cols = [(np.array([1, 2, 3], dtype=np.int64), np.array([False, True, False])), (np.array([7, 8, 9], dtype=np.int32), None)]
+    b = serde.serialize(cols, [1, 0], 1000)
+    raw = struct.pack("<i", 2) + struct.pack("<i", 3) + bytes([0b01000000]) + struct.pack("<qq", 1, 3) \
+        + struct.pack("<i", 3) + bytes([0]) + struct.pack("<iii", 7, 8, 9)
+    assert b == struct.pack("<ibii", 3, 0, len(raw), len(raw)) + raw
+    back = serde.deserialize(b, [1, 0])
+    assert back[0][0].tolist() == [1, 0, 3] and back[0][1].tolist() == [False, True, False] and back[1][0].tolist() == [7, 8, 9]
+    n = 2500
+    big = [((np.arange(n) * 3).astype(np.int64), (np.arange(n) % 5) == 0), (np.arange(n).astype(np.float64) / 3, None)]
+    rt = serde.deserialize(serde.serialize(big, [1, 2], 1000), [1, 2])
+    assert np.array_equal(rt[0][1], big[0][1]) and np.array_equal(rt[0][0][~big[0][1]], big[0][0][~big[0][1]]) and np.array_equal(rt[1][0], big[1][0])

@@ -124,3 +124,39 @@ def test_push_broadcast_and_round_robin_single_rank(gu):
         assert (np.sort(out[0][0][off:off + 2500]) % 4 == p).all()
         off += 2500
     x.close()
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("page_rows", [1000, 7, 100_000])
+def test_wire_codec_bytes_equal_the_reference_format(gu, mem, page_rows):
+    """gsql_serde_serialize produces, byte for byte, what the reference's PagesSerde writes (restated in oracle/serde.py):
+    framed pages of `page_rows` rows, NULL bit streams, non-NULL values only; deserialize inverts it.  Ragged last page,
+    page sizes that are not a multiple of 8, all-NULL and NULL-free columns."""
+    from galaxysql_b200 import api, native as N
+    from oracle import serde as oserde
+    n = 20_011 if page_rows != 7 else 1_003
+    a = ku.with_nulls((ku.rand_u64(n, 1) % np.uint64(1 << 31)).astype(np.int32) - (1 << 30), 0.2, 2)
+    b = ku.with_nulls((ku.rand_u64(n, 3) >> np.uint64(1)).astype(np.int64) - (1 << 62), 0.01, 4)
+    c = ((ku.rand_u64(n, 5) % np.uint64(100000)).astype(np.float64) / 7.0 - 5000.0, None)
+    d = (np.zeros(n, dtype=np.int64), np.ones(n, dtype=bool))                      # all NULL
+    cols = [a, b, c, d]
+    types = [N.T_INT32, N.T_INT64, N.T_FP64, N.T_INT64]
+    exp = oserde.serialize(cols, types, page_rows)
+    back = oserde.deserialize(exp, types)                                            # the restatement round-trips
+    assert ku.rows_multiset(back) == ku.rows_multiset(cols)
+    got = api.serde_serialize(gu.ctx(), gu.to_device(cols) if mem == "device" else cols, page_rows)
+    got_bytes = (got.cpu().numpy() if hasattr(got, "cpu") else got).tobytes()
+    assert len(got_bytes) == len(exp)
+    assert got_bytes == exp
+    dec = gu.to_numpy(api.serde_deserialize(gu.ctx(), got if mem == "device" else np.frombuffer(exp, dtype=np.uint8), types))
+    for (gv, gn), (ev, en) in zip(dec, cols):
+        en = np.zeros(n, bool) if en is None else en
+        assert np.array_equal(gn, en) and np.array_equal(gv[~en], ev[~en])
+    # empty batch, malformed input
+    assert len(api.serde_serialize(gu.ctx(), [(col[0][:0], None) for col in cols], page_rows)) == 0
+    with pytest.raises(N.GsqlError):
+        api.serde_deserialize(gu.ctx(), np.frombuffer(exp[:50], dtype=np.uint8), types)
+    bad = bytearray(exp)
+    bad[4] = 1                                                                       # ChunkCompression.COMPRESSED marker
+    with pytest.raises(N.GsqlError):
+        api.serde_deserialize(gu.ctx(), np.frombuffer(bytes(bad), dtype=np.uint8), types)
