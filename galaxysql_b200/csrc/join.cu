@@ -589,7 +589,9 @@ static gsql_status fj_partition(gsql_ctx *ctx, const DColSet &cols, const fj::La
     {
         KernelScope ks(ctx, name.c_str());
         FJ_DISPATCH_W(W, {
-            if (pipe) {
+            if (env_i64("GSQL_JOIN_SCATTER_DIRECT", 0)) {
+                fj::k_fj_scatter_direct<WW><<<g.nblocks, fj::THREADS, (size_t)P * 12, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
+            } else if (pipe) {
                     GSQL_CUDA(ctx, cudaFuncSetAttribute(fj::k_fj_scatter<WW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 fj::k_fj_scatter<WW, true><<<g.nblocks, fj::THREADS, smem, ctx->stream>>>(cols, L, g, offs.as<int64_t>(), out);
             } else {

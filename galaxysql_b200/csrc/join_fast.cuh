@@ -442,6 +442,44 @@ __global__ void __launch_bounds__(THREADS, 2) k_fj_scatter(const __grid_constant
     }
 }
 
+// ---- pass 2, variant without shared-memory staging (GSQL_JOIN_SCATTER_DIRECT=1): every row is stored straight to its
+// partition's run, 16 bytes at a time; the position comes from a per-block shared-memory counter per partition.  No block
+// barrier in the tile loop, no staging traffic; the 16-byte stores of neighbouring rows of a run meet in L2 (the write
+// frontier of a block is P sectors).  Measurement variant of r02 for the scatter's shared-memory bound (profiles/r01_ncu_summary.md).
+template <int W>
+__global__ void __launch_bounds__(THREADS, 2) k_fj_scatter_direct(const __grid_constant__ DColSet cols, const __grid_constant__ Layout L, PartGeom g,
+                                                               const int64_t *__restrict__ offs, unsigned long long *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long *base = reinterpret_cast<unsigned long long *>(smem_raw);  // P: first packed row of this block's run in partition p
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(base + g.P);             // P: rows of the block already placed there
+    for (int p = threadIdx.x; p < g.P; p += THREADS) {
+        base[p] = (unsigned long long)offs[(int64_t)p * g.nblocks + blockIdx.x];
+        cnt[p] = 0;
+    }
+    __syncthreads();
+    const int64_t r0 = (int64_t)blockIdx.x * g.chunk;
+    const int64_t r1 = r0 + g.chunk < g.rows ? r0 + g.chunk : g.rows;
+    for (int64_t t0 = r0; t0 < r1; t0 += TILE) {
+        unsigned long long w[RPT][W];
+        pack_tile<W>(cols, L, t0 + threadIdx.x, r1, w);
+#pragma unroll
+        for (int k = 0; k < RPT; k++) {
+            if (t0 + k * THREADS + threadIdx.x >= r1) continue;
+            const unsigned int pid = part_of(key_hash(w[k][0]), g.P);
+            const unsigned long long dst = base[pid] + atomicAdd(&cnt[pid], 1u);
+            if (W == 2) {
+                int4 v;
+                v.x = (int)(unsigned)w[k][0]; v.y = (int)(unsigned)(w[k][0] >> 32);
+                v.z = (int)(unsigned)w[k][W - 1]; v.w = (int)(unsigned)(w[k][W - 1] >> 32);
+                *reinterpret_cast<int4 *>(out + dst * 2) = v;
+            } else {
+#pragma unroll
+                for (int i = 0; i < W; i++) out[dst * W + i] = w[k][i];
+            }
+        }
+    }
+}
+
 static size_t scatter_smem_bytes(int W, int P, bool pipe) {
     return (size_t)TILE * W * 8 + (size_t)P * 8 * 2 + (size_t)P * 4 * 2 + (size_t)TILE * 2 + (pipe ? (size_t)2 * TILE * W * 8 : 0);
 }
