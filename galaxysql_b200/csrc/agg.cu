@@ -846,6 +846,15 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         if (use_reg) {  // register accumulators: NULL-free batch, <= 8 groups, fp64 sums (the Q1 shape)
             KernelScope ks(ctx, "agg_reg");
             int64_t tiles = div_up(P.rows, RG_TILE);
+            {  // bulk staging needs 16-byte aligned sources; tiles start at multiples of 1024 rows, so only the base counts
+                const bool no_bulk = getenv("GSQL_AGG_REG_NO_BULK") && atoi(getenv("GSQL_AGG_REG_NO_BULK"));
+                bool aligned = !no_bulk;
+                for (int u = 0; u < RP.nused; u++) {
+                    const DCol &c = P.in.c[RP.used_col[u]];
+                    if ((reinterpret_cast<uintptr_t>(c.data) + (uintptr_t)P.row0 * (uintptr_t)RP.used_w[u]) % 16 != 0) aligned = false;
+                }
+                RP.bulk = aligned ? 1 : 0;
+            }
             const size_t smem = (size_t)2 * RP.tile_bytes;
             const int per_sm = smem * 2 + 16384 <= 220 * 1024 ? 2 : 1;
             int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, tiles);

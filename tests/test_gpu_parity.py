@@ -639,6 +639,79 @@ def test_agg_reg_kernel_shapes_vs_oracle(gu, shape):
     gu.approx_rows_equal(got, exp, float_cols=fcols, key_cols=list(range(nk)), rtol=RTOL)
 
 
+@pytest.mark.parametrize("case", ["unaligned_views", "per_thread_staging_env", "nonfinite_values", "short_batches"])
+def test_agg_reg_staging_paths_and_nonfinite_values(gu, monkeypatch, case):
+    """k_agg_reg stages full tiles of 16-byte aligned batches by bulk copy (cp.async.bulk + mbarrier) and everything else —
+    the ragged last tile, a batch whose columns start off a 16-byte boundary, GSQL_AGG_REG_NO_BULK=1 — by per-thread
+    cp.async; all must agree with the oracle.  Its one-hot DFMA accumulate multiplies the other groups' share by 0.0, so a
+    row holding Inf / NaN takes the select form instead: the non-finite sums must come out Inf / NaN for THEIR groups only
+    and every other group must stay exact."""
+    import torch
+    from galaxysql_b200 import api, native as N
+    n = 700_001 if case != "short_batches" else 5_000
+    flag = (ku.rand_u64(n, 61) % np.uint64(3)).astype(np.int32)
+    status = (ku.rand_u64(n, 62) % np.uint64(2)).astype(np.int32)
+    qty = ((ku.rand_u64(n, 63) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
+    price = ((ku.rand_u64(n, 64) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    disc = (ku.rand_u64(n, 65) % np.uint64(11)).astype(np.float64) / 100.0
+    if case == "nonfinite_values":
+        g = flag * 2 + status
+        price[np.flatnonzero(g == 0)[[5, 4000, 90_000]]] = np.inf                     # group (0,0): +Inf
+        price[np.flatnonzero(g == 1)[[7]]] = np.nan                                   # group (0,1): NaN
+        price[np.flatnonzero(g == 2)[[11]]] = np.inf                                  # group (1,0): Inf - Inf = NaN
+        price[np.flatnonzero(g == 2)[[60_000]]] = -np.inf
+        qty[np.flatnonzero(g == 3)[[3]]] = -np.inf                                    # group (1,1): -Inf in another column
+    if case == "per_thread_staging_env":
+        monkeypatch.setenv("GSQL_AGG_REG_NO_BULK", "1")
+    cols = [(flag, None), (status, None), (qty, None), (price, None), (disc, None)]
+    derived = [(N.EXPR_MUL_1MINUS, 3, 4, 0)]
+    aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [5]), (N.AGG_AVG, [3]), (N.AGG_COUNT_STAR, [])]
+    ctx = gu.ctx()
+    ctx.profile(True)
+    ctx.profile_reset()
+    a = api.HashAgg(ctx, [0, 0, 2, 2, 2], [0, 1], aggs, 8, derived=derived)
+    keep = []
+    if case == "short_batches":
+        edges = [0, 1, 1024, 1025, 3073, n]   # below one tile, exactly one tile, one row, two tiles, ragged rest
+    else:
+        edges = [0, 300_000, n]
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        batch = []
+        for d, _ in cols:
+            if case == "unaligned_views":  # one leading element: fp64 columns start 8 bytes, INT columns 4 bytes off a 16-byte boundary
+                t = torch.from_numpy(np.concatenate([d[:1], d[lo:hi]])).cuda()
+                keep.append(t)
+                assert t[1:].data_ptr() % 16 != 0
+                batch.append((t[1:], None))
+            else:
+                batch.append((torch.from_numpy(np.ascontiguousarray(d[lo:hi])).cuda(), None))
+        a.consume(batch)
+    got = gu.to_numpy(a.result(N.MEM_DEVICE))
+    a.close()
+    prof = ctx.profile_dump()
+    ctx.profile(False)
+    assert "agg_reg" in prof and "agg_consume" not in prof, prof
+    with np.errstate(invalid="ignore"):
+        e1 = price * (1.0 - disc)
+        exp = orc.hash_agg(cols + [(e1, None)], [0, 1], [orc.AggCall(orc.AGG_SUM, [2]), orc.AggCall(orc.AGG_SUM, [3]), orc.AggCall(orc.AGG_SUM, [5]),
+                                                         orc.AggCall(orc.AGG_AVG, [3]), orc.AggCall(orc.AGG_COUNT_STAR)], 8)
+    def by_key(rows):
+        o = np.lexsort([np.asarray(rows[1][0]), np.asarray(rows[0][0])])
+        return [np.asarray(c[0])[o] for c in rows]
+    ga, ea = by_key(got), by_key(exp)
+    assert len(ga[0]) == 6
+    for c in (0, 1, 6):
+        assert np.array_equal(ga[c], ea[c]), c
+    for c in (2, 3, 4, 5):
+        gv, ev = ga[c].astype(np.float64), ea[c].astype(np.float64)
+        assert np.array_equal(np.isnan(gv), np.isnan(ev)), (c, gv, ev)
+        ok = ~np.isnan(ev)
+        assert np.allclose(gv[ok], ev[ok], rtol=RTOL, atol=0), (c, gv, ev)   # Inf == Inf with its sign; finite within 1e-6
+    if case == "nonfinite_values":
+        assert np.isposinf(ga[3][0]) and np.isnan(ga[3][1]) and np.isnan(ga[3][2]) and np.isneginf(ga[2][3])
+        assert np.all(np.isfinite(ga[3][3:])) and np.all(np.isfinite(ga[2][:3]))
+
+
 @pytest.mark.parametrize("shape", ["nullable_many_parts", "plain_int64_split_kernel", "plain_int32_split_kernel"])
 def test_agg_partition_prepass(gu, monkeypatch, shape):
     """High-cardinality group-by with the batch first reordered by table-slot range: the scalar k_agg_part_hist / _scatter
