@@ -845,34 +845,67 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
         const bool use_smem = !use_reg && !use_lane && first && a->fast.eligible && a->fast.enabled;
         if (use_reg) {  // register accumulators: NULL-free batch, <= 8 groups, fp64 sums (the Q1 shape)
             KernelScope ks(ctx, "agg_reg");
-            int64_t tiles = div_up(P.rows, RG_TILE);
-            {  // bulk staging needs 16-byte aligned sources; tiles start at multiples of 1024 rows, so only the base counts
-                const bool no_bulk = getenv("GSQL_AGG_REG_NO_BULK") && atoi(getenv("GSQL_AGG_REG_NO_BULK"));
-                bool aligned = !no_bulk;
-                for (int u = 0; u < RP.nused; u++) {
-                    const DCol &c = P.in.c[RP.used_col[u]];
-                    if ((reinterpret_cast<uintptr_t>(c.data) + (uintptr_t)P.row0 * (uintptr_t)RP.used_w[u]) % 16 != 0) aligned = false;
-                }
-                RP.bulk = aligned ? 1 : 0;
+            // bulk-copy staging needs 16-byte aligned sources; tiles start at multiples of 512 rows, so only the base counts
+            const bool no_bulk = getenv("GSQL_AGG_REG_NO_BULK") && atoi(getenv("GSQL_AGG_REG_NO_BULK"));
+            bool aligned = !no_bulk;
+            for (int u = 0; u < RP.nused; u++) {
+                const DCol &c = P.in.c[RP.used_col[u]];
+                if ((reinterpret_cast<uintptr_t>(c.data) + (uintptr_t)P.row0 * (uintptr_t)RP.used_w[u]) % 16 != 0) aligned = false;
             }
-            const size_t smem = (size_t)2 * RP.tile_bytes;
-            const int per_sm = smem * 2 + 16384 <= 220 * 1024 ? 2 : 1;
-            int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, tiles);
-            if (grid < 1) grid = 1;
+            const bool pipe_off = getenv("GSQL_AGG_REG_PIPE") && atoi(getenv("GSQL_AGG_REG_PIPE")) == 0;
+            if (aligned && !pipe_off) {  // k_agg_reg_pipe: 512-row tiles, 3-4 stages, full / empty mbarriers
+                RegPlan PP;
+                agg_reg_plan(&PP, a->spec, a->nkeys, a->naggs, a->spec.aggs, P.in, RGP_TILE);  // same verdict as RP, other tile size
+                const size_t budget2 = (size_t)104 * 1024;  // per block with two blocks per SM
+                int stages = (int)std::min<size_t>(RGP_MAX_STAGES, budget2 / PP.tile_bytes);
+                int per_sm = 2;
+                if (stages < 3) {
+                    per_sm = 1;
+                    stages = (int)std::min<size_t>(RGP_MAX_STAGES, ((size_t)208 * 1024) / PP.tile_bytes);
+                }
+                if (getenv("GSQL_AGG_REG_STAGES")) stages = std::max(3, std::min(stages, atoi(getenv("GSQL_AGG_REG_STAGES"))));
+                PP.stages = stages;
+                PP.bulk = 1;
+                const size_t smem = (size_t)stages * PP.tile_bytes;
+                int64_t tiles = div_up(P.rows, RGP_TILE);
+                int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, tiles);
+                if (grid < 1) grid = 1;
+#define GSQL_REGP_CASE(NS, GG)                                                                                                  \
+    {                                                                                                                          \
+        GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_reg_pipe<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
+        k_agg_reg_pipe<NS, GG><<<grid, RGP_THREADS, smem, ctx->stream>>>(P, PP);                                               \
+    }
+                switch (PP.nsrc) {
+                case 1: GSQL_REGP_CASE(1, 8) break;
+                case 2: GSQL_REGP_CASE(2, 8) break;
+                case 3: GSQL_REGP_CASE(3, 8) break;
+                case 4: GSQL_REGP_CASE(4, 8) break;
+                case 5: GSQL_REGP_CASE(5, 6) break;
+                default: GSQL_REGP_CASE(6, 6) break;
+                }
+#undef GSQL_REGP_CASE
+            } else {  // k_agg_reg: 1024-row tiles, two buffers, per-thread cp.async (or bulk copies + a block barrier per tile)
+                int64_t tiles = div_up(P.rows, RG_TILE);
+                RP.bulk = aligned ? 1 : 0;
+                const size_t smem = (size_t)2 * RP.tile_bytes;
+                const int per_sm = smem * 2 + 16384 <= 220 * 1024 ? 2 : 1;
+                int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, tiles);
+                if (grid < 1) grid = 1;
 #define GSQL_REG_CASE(NS, GG)                                                                                              \
     {                                                                                                                      \
         GSQL_CUDA(ctx, cudaFuncSetAttribute(k_agg_reg<NS, GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
         k_agg_reg<NS, GG><<<grid, RG_THREADS, smem, ctx->stream>>>(P, RP);                                                 \
     }
-            switch (RP.nsrc) {
-            case 1: GSQL_REG_CASE(1, 8) break;
-            case 2: GSQL_REG_CASE(2, 8) break;
-            case 3: GSQL_REG_CASE(3, 8) break;
-            case 4: GSQL_REG_CASE(4, 8) break;
-            case 5: GSQL_REG_CASE(5, 6) break;
-            default: GSQL_REG_CASE(6, 6) break;
-            }
+                switch (RP.nsrc) {
+                case 1: GSQL_REG_CASE(1, 8) break;
+                case 2: GSQL_REG_CASE(2, 8) break;
+                case 3: GSQL_REG_CASE(3, 8) break;
+                case 4: GSQL_REG_CASE(4, 8) break;
+                case 5: GSQL_REG_CASE(5, 6) break;
+                default: GSQL_REG_CASE(6, 6) break;
+                }
 #undef GSQL_REG_CASE
+            }
         } else if (use_lane) {
             KernelScope ks(ctx, "agg_lane");
             int64_t steps = div_up(P.rows, 32 * LA_R * LA_WARPS);

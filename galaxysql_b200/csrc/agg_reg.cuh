@@ -51,7 +51,9 @@ struct RegPlan {
     int64_t rf_lo, rf_hi;
     int32_t agg_src[GSQL_MAX_AGGS];  // per aggregate: the sum it reports, -1 for COUNT / COUNT(*)
     int32_t bulk;                    // 1: every staged column is 16-byte aligned at row0 -> full tiles arrive by bulk copy
-    int32_t bulk_bytes;              // bytes one full tile brings in (sum of RG_TILE * used_w)
+    int32_t bulk_bytes;              // bytes one full tile brings in (sum of tile rows * used_w)
+    int32_t stages;                  // k_agg_reg_pipe: tile buffers (3 or 4)
+    int32_t pad2;
 };
 
 __device__ __forceinline__ void rg_cp_async_4(void *smem_dst, const void *gsrc) {
@@ -87,13 +89,14 @@ __device__ __forceinline__ void rg_bulk_load(void *smem_dst, const void *gsrc, u
                  : "memory");
 }
 // One FULL tile, called by one thread: arm the stage's barrier with the tile's byte count, then one copy per column.
+template <int TILE_ROWS>
 __device__ __forceinline__ void rg_bulk_issue(const AggParams &P, const RegPlan &L, int64_t t0, unsigned char *buf, unsigned long long *bar, uint64_t pol) {
     rg_mbar_expect_tx(bar, (uint32_t)L.bulk_bytes);
 #pragma unroll 1
     for (int u = 0; u < L.nused; u++) {
         const DCol &c = P.in.c[L.used_col[u]];
         const uint32_t w = (uint32_t)L.used_w[u];
-        rg_bulk_load(buf + L.used_off[u], reinterpret_cast<const unsigned char *>(c.data) + (size_t)(P.row0 + t0) * w, RG_TILE * w, bar, pol);
+        rg_bulk_load(buf + L.used_off[u], reinterpret_cast<const unsigned char *>(c.data) + (size_t)(P.row0 + t0) * w, TILE_ROWS * w, bar, pol);
     }
 }
 
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant
         const int64_t s0 = tl * RG_TILE;
         unsigned char *dst = rg_smem + (size_t)st * L.tile_bytes;
         if (bulk && P.rows - s0 >= RG_TILE) {
-            if (tid == 0) rg_bulk_issue(P, L, s0, dst, &tile_bar[st], pol_stream);
+            if (tid == 0) rg_bulk_issue<RG_TILE>(P, L, s0, dst, &tile_bar[st], pol_stream);
             rg_cp_async_commit();
         } else {
             rg_prefetch(P, L, s0, dst);
@@ -393,6 +396,345 @@ __global__ void __launch_bounds__(RG_THREADS, 2) k_agg_reg(const __grid_constant
     }
 }
 
+
+// ================================================================================================ pipelined variant
+// k_agg_reg_pipe: the same algorithm for batches whose staged columns are 16-byte aligned, rebuilt around what the r02
+// profile of k_agg_reg showed once the loads were off the critical path (issue 56 %; stalls: fixed-latency `wait` 29 %,
+// short scoreboard 17 %, the per-tile block barrier 15 %):
+//   * S = 3-4 stages of 512-row tiles, a full / empty mbarrier pair per stage: a warp that finishes a tile releases it and
+//     moves on — no block barrier; thread 0 refills a stage two tiles after it was consumed, so a straggling warp delays
+//     nobody until it is a whole tile behind;
+//   * the rows of a tile are handled in three unrolled passes — keys and filter for all rows, (rarely) the dictionary /
+//     generic slow path, values and accumulate for all rows — so the shared-memory loads of the tile's rows are in flight
+//     together instead of one row's dependent chain after the other;
+//   * shared memory is addressed with explicit 32-bit addresses computed once per tile (ld.shared), not through generic
+//     pointers re-derived per row (S2UR SR_CgaCtaId + ULEA + LDC in the old SASS).
+// The ragged last tile is loaded synchronously by its owner block after the pipeline has drained.
+constexpr int RGP_THREADS = 256;
+constexpr int RGP_RPT = 2;
+constexpr int RGP_TILE = RGP_THREADS * RGP_RPT;  // 512 rows
+constexpr int RGP_MAX_STAGES = 4;
+
+// (memory clobber: the compiler keeps them after the mbarrier wait / the tail's plain stores; ptxas still schedules the
+// resulting LDS freely among the arithmetic)
+__device__ __forceinline__ double rg_lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long rg_lds_u64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int rg_lds_u32(uint32_t a) {
+    unsigned int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// A row whose key found no place in the block's dictionary: the generic table, right here (cold).
+__device__ __noinline__ void rg_fallback_row(const AggParams &P, const RegPlan &L, unsigned long long key, int64_t r) {
+    int64_t kv[GSQL_MAX_KEYS];
+    bool kn[GSQL_MAX_KEYS];
+    reg_decode_key(P, L, key, kv, kn);
+    const int g2 = find_group_kv(P, kv, kn, digest_of_keys(P, kv, kn));
+    if (g2 < 0) {
+        unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
+        P.overflow_rows[o] = r;
+    } else {
+        for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], g2, r);
+    }
+}
+
+// Warp-cooperative insertion of the keys this warp has not seen (same protocol as in k_agg_reg: one distinct key at a
+// time, lane 0 takes the block's lock).  Every lane of the warp must call it.  gid: -1 unknown -> group index, or -2 when
+// the dictionary is full.
+template <int G>
+__device__ __forceinline__ void rg_dict_insert(bool pass, int &gid, unsigned long long key, unsigned long long (&kk)[G], int &ng,
+                                               unsigned long long *skey, int *s_ng, int *s_lock, int lane) {
+    unsigned need = __ballot_sync(0xffffffffu, pass && gid < 0);
+    while (need) {
+        const int leader = __ffs(need) - 1;
+        const unsigned long long lk = __shfl_sync(0xffffffffu, key, leader);
+        int got = -1;
+        if (lane == 0) {
+            while (atomicCAS(s_lock, 0, 1) != 0) {}
+            const int cur = *reinterpret_cast<volatile int *>(s_ng);
+            for (int g = 0; g < cur; g++)
+                if (*reinterpret_cast<volatile unsigned long long *>(&skey[g]) == lk) got = g;
+            if (got < 0 && cur < G) {
+                *reinterpret_cast<volatile unsigned long long *>(&skey[cur]) = lk;
+                __threadfence_block();
+                *reinterpret_cast<volatile int *>(s_ng) = cur + 1;
+                got = cur;
+            } else if (got < 0) {
+                got = -2;
+            }
+            __threadfence_block();
+            atomicExch(s_lock, 0);
+        }
+        got = __shfl_sync(0xffffffffu, got, 0);
+        if (pass && gid < 0 && key == lk) gid = got;
+        if (got >= 0) {
+            const int now = *reinterpret_cast<volatile int *>(s_ng);
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (g < now) kk[g] = *reinterpret_cast<volatile unsigned long long *>(&skey[g]);
+            ng = now;
+        }
+        need = __ballot_sync(0xffffffffu, pass && gid == -1);
+    }
+}
+
+// shared-address forms of the mbarrier / bulk-copy helpers (addresses computed once per kernel)
+__device__ __forceinline__ void rg_mbar_expect_tx_a(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rg_mbar_arrive_a(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void rg_mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void rg_bulk_load_a(uint32_t smem_dst, const void *gsrc, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst), "l"(gsrc),
+                 "r"(bytes), "r"(bar), "l"(pol)
+                 : "memory");
+}
+
+template <int NSRC, int G>
+__global__ void __launch_bounds__(RGP_THREADS, 2) k_agg_reg_pipe(const __grid_constant__ AggParams P, const __grid_constant__ RegPlan L) {
+    extern __shared__ __align__(128) unsigned char rg_smem[];  // L.stages tile buffers
+    __shared__ unsigned long long skey[G];
+    __shared__ int s_ng, s_lock;
+    __shared__ double red[RGP_THREADS / 32][G][NSRC];
+    __shared__ unsigned long long redc[RGP_THREADS / 32][G];
+    __shared__ __align__(8) unsigned long long bar_full[RGP_MAX_STAGES], bar_empty[RGP_MAX_STAGES];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int S = L.stages, D = S - 2;  // prefetch distance: a stage is refilled two tiles after it was consumed
+    if (tid == 0) {
+        s_ng = 0;
+        s_lock = 0;
+        for (int s = 0; s < S; s++) {
+            rg_mbar_init(&bar_full[s], 1);
+            rg_mbar_init(&bar_empty[s], RGP_THREADS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // Issuing a bulk copy is slow for the issuing thread (one thread issuing a tile's 7 copies made its warp the block's
+    // straggler: 9.5 vs 7.4 ms on the Q1 shape), so the work is spread: lane 0 of warp u copies staged column u, thread 0
+    // also arms the tile's barrier.  (A complete_tx that lands before the expect_tx is legal: the phase cannot complete
+    // before that arrival.)
+    const bool issuer = lane == 0 && warp < L.nused;
+    const unsigned char *src_next = nullptr;  // issuer: this block's next tile of its column
+    uint32_t col_bytes = 0, dst_off = 0;
+    uint64_t src_stride = 0, pol_stream = 0;
+    if (issuer) {
+        const DCol &c = P.in.c[L.used_col[warp]];
+        const uint32_t w = (uint32_t)L.used_w[warp];
+        col_bytes = RGP_TILE * w;
+        dst_off = (uint32_t)L.used_off[warp];
+        src_next = reinterpret_cast<const unsigned char *>(c.data) + (size_t)P.row0 * w + (size_t)blockIdx.x * col_bytes;
+        src_stride = (uint64_t)gridDim.x * col_bytes;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+    }
+    double acc[G][NSRC];
+    unsigned int cnt[G];
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        cnt[g] = 0;
+#pragma unroll
+        for (int j = 0; j < NSRC; j++) acc[g][j] = 0.0;
+    }
+    __syncthreads();
+    unsigned long long fallback_rows = 0;
+    unsigned long long kk[G];  // this thread's copy of the block's key dictionary
+    int ng = 0;
+    const int64_t nfull = P.rows / RGP_TILE;  // full tiles of the batch; tile j of this block is blockIdx.x + j * gridDim.x
+    const int mine = nfull > blockIdx.x ? (int)((nfull - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    const uint32_t smem0 = rg_smem_u32(rg_smem), full_a = rg_smem_u32(bar_full), empty_a = rg_smem_u32(bar_empty), sng_a = rg_smem_u32(&s_ng);
+    const uint32_t tile_bytes = (uint32_t)L.tile_bytes;
+    auto issue = [&](int stage) {  // issuer threads only; tiles are issued in this block's tile order
+        if (tid == 0) rg_mbar_expect_tx_a(full_a + 8u * stage, (uint32_t)L.bulk_bytes);
+        rg_bulk_load_a(smem0 + (uint32_t)stage * tile_bytes + dst_off, src_next, col_bytes, full_a + 8u * stage, pol_stream);
+        src_next += src_stride;
+    };
+
+    // one tile's rows: keys + filter, slow path when some key is new, values + accumulate.  `a8` / `a4` are the shared
+    // addresses of this thread's first row in a region of 8- / 4-byte cells; row k sits RGP_THREADS cells further.
+    auto consume = [&](uint32_t base, int64_t t0, int left) {
+        const uint32_t a8 = base + (uint32_t)tid * 8u, a4 = base + (uint32_t)tid * 4u;
+        {  // refresh the register copy of the dictionary when another warp has added keys
+            const int now = (int)rg_lds_u32(sng_a);
+            if (now != ng) {
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (g < now) kk[g] = *reinterpret_cast<volatile unsigned long long *>(&skey[g]);
+                ng = now;
+            }
+        }
+        unsigned long long key[RGP_RPT];
+        bool pass[RGP_RPT];
+        int gid[RGP_RPT];
+        bool unknown = false;
+#pragma unroll
+        for (int k = 0; k < RGP_RPT; k++) {
+            const uint32_t o8 = (uint32_t)k * RGP_THREADS * 8u, o4 = (uint32_t)k * RGP_THREADS * 4u;
+            pass[k] = k * RGP_THREADS + tid < left;
+            key[k] = L.key_w[0] == 4 ? (unsigned long long)rg_lds_u32(a4 + (uint32_t)L.key_off[0] + o4) : rg_lds_u64(a8 + (uint32_t)L.key_off[0] + o8);
+            if (L.nkeys == 2) key[k] |= (unsigned long long)rg_lds_u32(a4 + (uint32_t)L.key_off[1] + o4) << 32;
+            if (L.rf_u >= 0) {
+                const long long x = L.rf_w == 4 ? (long long)(int)rg_lds_u32(a4 + (uint32_t)L.rf_off + o4) : (long long)rg_lds_u64(a8 + (uint32_t)L.rf_off + o8);
+                pass[k] = pass[k] && ((x >= L.rf_lo && x <= L.rf_hi) != (L.rf_neg != 0));
+            }
+            gid[k] = -1;
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (g < ng && kk[g] == key[k]) gid[k] = g;
+            unknown = unknown || (pass[k] && gid[k] < 0);
+        }
+        if (__any_sync(0xffffffffu, unknown)) {  // first tiles only (or a dictionary that is full)
+#pragma unroll
+            for (int k = 0; k < RGP_RPT; k++) {
+                rg_dict_insert<G>(pass[k], gid[k], key[k], kk, ng, skey, &s_ng, &s_lock, lane);
+                if (pass[k] && gid[k] == -2) {
+                    fallback_rows++;
+                    rg_fallback_row(P, L, key[k], P.row0 + t0 + k * RGP_THREADS + tid);
+                    pass[k] = false;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < RGP_RPT; k++) {
+            const uint32_t o8 = (uint32_t)k * RGP_THREADS * 8u;
+            double v[NSRC];
+#pragma unroll
+            for (int j = 0; j < NSRC; j++) {
+                const RegSrc &sr = L.src[j];
+                double x = rg_lds_f64(a8 + (uint32_t)sr.oa + o8);
+                if (sr.kind != 0) {  // block-uniform
+                    x = x * (1.0 - rg_lds_f64(a8 + (uint32_t)sr.ob + o8));
+                    if (sr.kind == GSQL_EXPR_MUL_1MINUS_1PLUS) x = x * (1.0 + rg_lds_f64(a8 + (uint32_t)sr.oc + o8));
+                }
+                v[j] = x;
+            }
+            const int gk = pass[k] ? gid[k] : -1;
+            int worst = 0;
+#pragma unroll
+            for (int j = 0; j < NSRC; j++) worst = max(worst, __double2hiint(v[j]) & 0x7ff00000);
+            if (worst != 0x7ff00000) rg_accumulate_onehot<NSRC, G>(acc, cnt, v, gk);
+            else rg_accumulate<NSRC, G, 0>(acc, cnt, v, gk);
+        }
+    };
+
+    if (issuer) {  // prologue: the first D tiles
+        for (int j = 0; j < D && j < mine; j++) issue(j);
+    }
+    int st = 0;            // stage of tile j
+    uint32_t ph = 0;       // its parity: (j / S) & 1
+    int pst = D;           // issuers: the stage tile j + D goes to, == (j - 2) mod S ...
+    uint32_t pph = 1;      // ... and, from j = 2 on, the parity of that stage's release by tile j - 2: ((j - 2) / S) & 1
+                           // (toggled at every wrap of pst; the first wrap, at j = 1, brings it to 0)
+    int64_t t0 = (int64_t)blockIdx.x * RGP_TILE;
+    const int64_t t_stride = (int64_t)gridDim.x * RGP_TILE;
+    // the ragged last tile of the batch is one more iteration of its owner block: loaded with plain loads after the
+    // pipeline has drained (one tile per batch at most)
+    const int tail = (int)(P.rows - nfull * RGP_TILE);
+    const int iters = mine + ((tail > 0 && (int64_t)blockIdx.x == nfull % gridDim.x) ? 1 : 0);
+    for (int j = 0; j < iters; j++, t0 += t_stride) {
+        const bool full = j < mine;
+        if (full) {
+            if (issuer && j + D < mine) {
+                if (j >= 2) rg_mbar_wait_a(empty_a + 8u * pst, pph);  // every warp has released tile j - 2
+                issue(pst);
+            }
+            if (++pst == S) { pst = 0; pph ^= 1u; }
+            rg_mbar_wait_a(full_a + 8u * st, ph);
+        } else {
+            __syncthreads();  // every warp is done with every stage; nothing is in flight (all issued tiles were consumed)
+            t0 = nfull * RGP_TILE;
+            for (int u = 0; u < L.nused; u++) {
+                const DCol &c = P.in.c[L.used_col[u]];
+                unsigned char *dst = rg_smem + (size_t)st * L.tile_bytes + L.used_off[u];
+#pragma unroll
+                for (int k = 0; k < RGP_RPT; k++) {
+                    const int i = k * RGP_THREADS + tid;
+                    if (i < tail) {
+                        if (L.used_w[u] == 4) reinterpret_cast<int *>(dst)[i] = reinterpret_cast<const int *>(c.data)[P.row0 + t0 + i];
+                        else reinterpret_cast<long long *>(dst)[i] = reinterpret_cast<const long long *>(c.data)[P.row0 + t0 + i];
+                    }
+                }
+            }
+            __syncwarp();  // a thread reads only the cells it wrote
+        }
+        consume(smem0 + (uint32_t)st * tile_bytes, t0, full ? RGP_TILE : tail);
+        if (full) {
+            __syncwarp();
+            if (lane == 0) rg_mbar_arrive_a(empty_a + 8u * st);
+            if (++st == S) { st = 0; ph ^= 1u; }
+        }
+    }
+    if (fallback_rows) atomicAdd(&P.counters[C_FALLBACK], fallback_rows);
+    // ---- merge (as in k_agg_reg): warp shuffles, then shared memory, then one thread per group into the global table
+    __syncthreads();
+    const int ngf = s_ng;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        if (g >= ngf) break;
+        unsigned int c = cnt[g];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0) redc[warp][g] = c;
+#pragma unroll
+        for (int j = 0; j < NSRC; j++) {
+            const double sm = warp_sum_f64(acc[g][j]);
+            if (lane == 0) red[warp][g][j] = sm;
+        }
+    }
+    __syncthreads();
+    if (tid < ngf) {
+        const int g = tid;
+        unsigned long long c = 0;
+        double sums[NSRC];
+#pragma unroll
+        for (int j = 0; j < NSRC; j++) sums[j] = 0.0;
+        for (int w = 0; w < RGP_THREADS / 32; w++) {
+            c += redc[w][g];
+#pragma unroll
+            for (int j = 0; j < NSRC; j++) sums[j] += red[w][g][j];
+        }
+        if (c) {
+            int64_t kv[GSQL_MAX_KEYS];
+            bool kn[GSQL_MAX_KEYS];
+            reg_decode_key(P, L, skey[g], kv, kn);
+            const int gl = find_group_kv(P, kv, kn, digest_of_keys(P, kv, kn), true);
+            for (int a = 0; a < P.naggs; a++) {
+                const AggDev &ag = P.agg[a];
+                double sv = 0.0;
+#pragma unroll
+                for (int j = 0; j < NSRC; j++)
+                    if (L.agg_src[a] == j) sv = sums[j];
+                switch (ag.kind) {
+                case GSQL_AGG_COUNT_STAR: case GSQL_AGG_COUNT:
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&ag.l[gl]), c);
+                    break;
+                case GSQL_AGG_SUM:
+                    atomicAdd(&ag.d[gl], sv);
+                    ag.has[gl] = 1;
+                    break;
+                default:  // AVG
+                    atomicAdd(&ag.d[gl], sv);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&ag.l[gl]), c);
+                    ag.has[gl] = 1;
+                    break;
+                }
+            }
+        }
+    }
+}
+
 }  // namespace
 
 struct AggReg {
@@ -427,7 +769,7 @@ static void agg_reg_check(AggReg *F, const gsql_agg_spec &spec, int nkeys, int n
 }
 
 // Per-batch plan (NULL buffers are a property of the batch).  false = this batch takes another kernel.
-static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int naggs, const gsql_agg_call *aggs, const DColSet &in) {
+static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int naggs, const gsql_agg_call *aggs, const DColSet &in, int tile_rows = RG_TILE) {
     RegPlan &L = *Lp;
     memset(&L, 0, sizeof(L));
     L.nkeys = nkeys;
@@ -497,7 +839,7 @@ static bool agg_reg_plan(RegPlan *Lp, const gsql_agg_spec &spec, int nkeys, int 
         for (int u = 0; u < L.nused; u++)
             if ((L.used_w[u] == 8) == (pass == 0)) {
                 L.used_off[u] = off;
-                off += RG_TILE * L.used_w[u];
+                off += tile_rows * L.used_w[u];
             }
     L.tile_bytes = (off + 15) & ~15;
     L.bulk_bytes = off;

@@ -639,16 +639,18 @@ def test_agg_reg_kernel_shapes_vs_oracle(gu, shape):
     gu.approx_rows_equal(got, exp, float_cols=fcols, key_cols=list(range(nk)), rtol=RTOL)
 
 
-@pytest.mark.parametrize("case", ["unaligned_views", "per_thread_staging_env", "nonfinite_values", "short_batches"])
+@pytest.mark.parametrize("case", ["unaligned_views", "per_thread_staging_env", "two_buffer_bulk_env", "three_stage_env", "nonfinite_values",
+                                  "short_batches", "short_batches_two_buffer"])
 def test_agg_reg_staging_paths_and_nonfinite_values(gu, monkeypatch, case):
-    """k_agg_reg stages full tiles of 16-byte aligned batches by bulk copy (cp.async.bulk + mbarrier) and everything else —
-    the ragged last tile, a batch whose columns start off a 16-byte boundary, GSQL_AGG_REG_NO_BULK=1 — by per-thread
-    cp.async; all must agree with the oracle.  Its one-hot DFMA accumulate multiplies the other groups' share by 0.0, so a
+    """A 16-byte aligned batch runs on k_agg_reg_pipe (512-row tiles by bulk copy, 3-4 stages with full / empty mbarriers,
+    ragged last tile by plain loads); GSQL_AGG_REG_PIPE=0 selects k_agg_reg with bulk copies into two buffers and a block
+    barrier per tile; a batch whose columns start off a 16-byte boundary, or GSQL_AGG_REG_NO_BULK=1, k_agg_reg with
+    per-thread cp.async.  All must agree with the oracle.  Its one-hot DFMA accumulate multiplies the other groups' share by 0.0, so a
     row holding Inf / NaN takes the select form instead: the non-finite sums must come out Inf / NaN for THEIR groups only
     and every other group must stay exact."""
     import torch
     from galaxysql_b200 import api, native as N
-    n = 700_001 if case != "short_batches" else 5_000
+    n = 700_001 if not case.startswith("short_batches") else 5_000
     flag = (ku.rand_u64(n, 61) % np.uint64(3)).astype(np.int32)
     status = (ku.rand_u64(n, 62) % np.uint64(2)).astype(np.int32)
     qty = ((ku.rand_u64(n, 63) % np.uint64(50)) + np.uint64(1)).astype(np.float64)
@@ -663,6 +665,10 @@ def test_agg_reg_staging_paths_and_nonfinite_values(gu, monkeypatch, case):
         qty[np.flatnonzero(g == 3)[[3]]] = -np.inf                                    # group (1,1): -Inf in another column
     if case == "per_thread_staging_env":
         monkeypatch.setenv("GSQL_AGG_REG_NO_BULK", "1")
+    if case in ("two_buffer_bulk_env", "short_batches_two_buffer"):
+        monkeypatch.setenv("GSQL_AGG_REG_PIPE", "0")
+    if case == "three_stage_env":
+        monkeypatch.setenv("GSQL_AGG_REG_STAGES", "3")
     cols = [(flag, None), (status, None), (qty, None), (price, None), (disc, None)]
     derived = [(N.EXPR_MUL_1MINUS, 3, 4, 0)]
     aggs = [(N.AGG_SUM, [2]), (N.AGG_SUM, [3]), (N.AGG_SUM, [5]), (N.AGG_AVG, [3]), (N.AGG_COUNT_STAR, [])]
@@ -671,8 +677,8 @@ def test_agg_reg_staging_paths_and_nonfinite_values(gu, monkeypatch, case):
     ctx.profile_reset()
     a = api.HashAgg(ctx, [0, 0, 2, 2, 2], [0, 1], aggs, 8, derived=derived)
     keep = []
-    if case == "short_batches":
-        edges = [0, 1, 1024, 1025, 3073, n]   # below one tile, exactly one tile, one row, two tiles, ragged rest
+    if case.startswith("short_batches"):
+        edges = [0, 1, 1024, 1025, 3073, n]   # one row, 1023 rows, one row, 2048 rows (whole tiles only), ragged rest
     else:
         edges = [0, 300_000, n]
     for lo, hi in zip(edges[:-1], edges[1:]):
