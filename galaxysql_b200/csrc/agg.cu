@@ -94,32 +94,55 @@ __host__ __device__ __forceinline__ double dbl_unsortable(long long s, bool for_
 
 __device__ __forceinline__ bool in_null(const DCol &c, int64_t r) { return c.nulls != nullptr && c.nulls[r] != 0; }
 
+// The key helpers below are templated on the number of group keys: NK = 1..3 unrolls their loops over kv[] / kn[] so
+// that the arrays live in registers; NK = 0 is the dynamic form (P.nkeys at run time), which indexes the arrays in a
+// rolled loop and therefore keeps them in LOCAL memory — an 80-byte stack frame per thread that, at 2048 threads per SM,
+// does not fit L1: the r02 profile of the generic kernel showed 1.8 evict-first sector misses and 0.9 sector writes per
+// row at L2 from that traffic alone, ~70 % of its DRAM reads.  The row loops are instantiated for NK = 1, 2, 3.
 // Table digest of a canonical key image: the key itself for a single key column (exact), a 64-bit mix otherwise.
+template <int NK = 0>
 __device__ __forceinline__ unsigned long long digest_of_keys(const AggParams &P, const int64_t (&kv)[GSQL_MAX_KEYS], const bool (&kn)[GSQL_MAX_KEYS]) {
     if (P.exact) return (unsigned long long)kv[0];
     unsigned long long h = 0x243F6A8885A308D3ULL;
+    if constexpr (NK > 0) {
+#pragma unroll
+        for (int c = 0; c < NK; c++)
+            h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (kn[c] ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+    } else {
 #pragma unroll 1
-    for (int c = 0; c < P.nkeys; c++)
-        h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (kn[c] ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+        for (int c = 0; c < P.nkeys; c++)
+            h = gsql_fmix64(h ^ (unsigned long long)kv[c]) + (kn[c] ? 0xD6E8FEB86659FD93ULL : 0x9E3779B97F4A7C15ULL) * (unsigned)(c + 1);
+    }
     if (h == DIGEST_EMPTY) h ^= 1;
     return h;
 }
 
 // Canonical key image of input row r (values + NULL flags) and its table digest.
+template <int NK = 0>
 __device__ __forceinline__ unsigned long long load_group_key(const AggParams &P, int64_t r, int64_t (&kv)[GSQL_MAX_KEYS], bool (&kn)[GSQL_MAX_KEYS]) {
+    if constexpr (NK > 0) {
+#pragma unroll
+        for (int c = 0; c < NK; c++) {
+            KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
+            kn[c] = k.is_null;
+            kv[c] = canon_key(k, P.keys.utype[c]);
+        }
+    } else {
 #pragma unroll 1
-    for (int c = 0; c < P.nkeys; c++) {
-        KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
-        kn[c] = k.is_null;
-        kv[c] = canon_key(k, P.keys.utype[c]);
+        for (int c = 0; c < P.nkeys; c++) {
+            KeyVal k = gsql_load_key(P.keys.c[c], r, P.keys.utype[c]);
+            kn[c] = k.is_null;
+            kv[c] = canon_key(k, P.keys.utype[c]);
+        }
     }
-    return digest_of_keys(P, kv, kn);
+    return digest_of_keys<NK>(P, kv, kn);
 }
 
 // Finds or creates the group with key (kv, kn) / digest d.  Returns gid >= 0, or -1 when the table is full.
+template <int NK = 0>
 __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (&kv)[GSQL_MAX_KEYS], const bool (&kn)[GSQL_MAX_KEYS],
                                              unsigned long long d, bool ignore_cap = false) {
-    if (P.nkeys == 0) return 0;
+    if (NK == 0 && P.nkeys == 0) return 0;
     uint64_t s;
     bool dedicated = false;
     if (P.exact) {
@@ -155,6 +178,12 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
             if ((int64_t)gid >= P.garr) {  // cannot happen while the host grows after every launch (slack covers one launch's merges):
                 P.counters[C_FATAL] = 1;   // never write out of bounds — the host turns this into an error
                 gid = (int)(P.garr - 1);
+            } else if constexpr (NK > 0) {
+#pragma unroll
+                for (int c = 0; c < NK; c++) {
+                    P.gkey[c][gid] = kv[c];
+                    P.gnull[c][gid] = kn[c] ? 1 : 0;
+                }
             } else {
                 for (int c = 0; c < P.nkeys; c++) {
                     P.gkey[c][gid] = kv[c];
@@ -171,10 +200,21 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
             if (P.exact) return gid;
             __threadfence();
             bool eq = true;
-            for (int c = 0; c < P.nkeys && eq; c++) {
-                bool gn = *reinterpret_cast<volatile uint8_t *>(&P.gnull[c][gid]) != 0;
-                long long gv = *reinterpret_cast<volatile long long *>(&P.gkey[c][gid]);
-                if (gn != kn[c] || (!gn && gv != kv[c])) eq = false;
+            if constexpr (NK > 0) {
+#pragma unroll
+                for (int c = 0; c < NK; c++) {
+                    if (eq) {
+                        bool gn = *reinterpret_cast<volatile uint8_t *>(&P.gnull[c][gid]) != 0;
+                        long long gv = *reinterpret_cast<volatile long long *>(&P.gkey[c][gid]);
+                        if (gn != kn[c] || (!gn && gv != kv[c])) eq = false;
+                    }
+                }
+            } else {
+                for (int c = 0; c < P.nkeys && eq; c++) {
+                    bool gn = *reinterpret_cast<volatile uint8_t *>(&P.gnull[c][gid]) != 0;
+                    long long gv = *reinterpret_cast<volatile long long *>(&P.gkey[c][gid]);
+                    if (gn != kn[c] || (!gn && gv != kv[c])) eq = false;
+                }
             }
             if (eq) return gid;
         }
@@ -182,12 +222,13 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
     }
 }
 
+template <int NK = 0>
 __device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
-    if (P.nkeys == 0) return 0;
+    if (NK == 0 && P.nkeys == 0) return 0;
     int64_t kv[GSQL_MAX_KEYS];
     bool kn[GSQL_MAX_KEYS];
-    unsigned long long d = load_group_key(P, r, kv, kn);
-    return find_group_kv(P, kv, kn, d);
+    unsigned long long d = load_group_key<NK>(P, r, kv, kn);
+    return find_group_kv<NK>(P, kv, kn, d);
 }
 
 __device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {  // streaming (evict-first) reads: every input value is used once
@@ -294,17 +335,32 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     }
 }
 
+// The generic row loop.  Its trip count is warp-uniform and the warp is brought back together twice per row
+// (__syncwarp): the probe of the table is divergent by nature, and without the explicit reconvergence the lanes drifted
+// apart for good — the r02 profile showed the key and value loads of the next rows executing with 12-19 active lanes,
+// each fetching its own 32-byte sector (0.97 L2 sectors per row per column instead of 0.25; 62 instead of 16 bytes of
+// DRAM reads per row on the C5 share).
+template <int NK>
 __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ AggParams P) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.rows; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = P.row_list ? P.row_list[i] : P.row0 + i;
-        if (!row_passes(P, r)) continue;
-        int gid = find_group(P, r);
-        if (gid < 0) {
-            unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
-            P.overflow_rows[o] = r;
-            continue;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + (threadIdx.x - lane); base < P.rows; base += stride) {
+        const int64_t i = base + lane;
+        const bool live = i < P.rows;
+        const int64_t r = live ? (P.row_list ? P.row_list[i] : P.row0 + i) : 0;
+        const bool pass = live && row_passes(P, r);
+        int gid = -1;
+        if (pass) gid = find_group<NK>(P, r);
+        __syncwarp();  // the aggregates' input loads below are issued by the whole warp again: coalesced
+        if (pass) {
+            if (gid < 0) {
+                unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
+                P.overflow_rows[o] = r;
+            } else {
+                for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r);
+            }
         }
-        for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r);
+        __syncwarp();  // ... and so are the key loads of the next row
     }
 }
 
@@ -323,24 +379,27 @@ struct APartOut {
     uint8_t *nulls[GSQL_MAX_COLS];
 };
 
+template <int NK>
 __device__ __forceinline__ int agg_part_of(const AggParams &P, int64_t r, int nparts) {
     int64_t kv[GSQL_MAX_KEYS];
     bool kn[GSQL_MAX_KEYS];
-    unsigned long long d = load_group_key(P, r, kv, kn);
+    unsigned long long d = load_group_key<NK>(P, r, kv, kn);
     return (int)__umul64hi(gsql_fmix64(d), (uint64_t)nparts);  // slot = mulhi(fmix64(d), nslots): partition = slot range
 }
 
+template <int NK>
 __global__ void __launch_bounds__(256) k_agg_part_hist(const __grid_constant__ AggParams P, APart G, int64_t *__restrict__ hist) {
     extern __shared__ unsigned int sh_part[];
     for (int i = threadIdx.x; i < G.nparts; i += 256) sh_part[i] = 0;
     __syncthreads();
     int64_t r0 = (int64_t)blockIdx.x * G.chunk;
     int64_t r1 = r0 + G.chunk < P.rows ? r0 + G.chunk : P.rows;
-    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) atomicAdd(&sh_part[agg_part_of(P, r, G.nparts)], 1u);
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) atomicAdd(&sh_part[agg_part_of<NK>(P, r, G.nparts)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < G.nparts; i += 256) hist[(int64_t)i * G.nblocks + blockIdx.x] = sh_part[i];
 }
 
+template <int NK>
 __global__ void __launch_bounds__(256)
     k_agg_part_scatter(const __grid_constant__ AggParams P, APart G, const int64_t *__restrict__ offs, const __grid_constant__ APartOut O) {
     extern __shared__ unsigned long long cur_part[];
@@ -351,7 +410,7 @@ __global__ void __launch_bounds__(256)
     for (int64_t base = r0; base < r1; base += 256) {
         int64_t r = base + threadIdx.x;
         bool live = r < r1;
-        int p = live ? agg_part_of(P, r, G.nparts) : -1;
+        int p = live ? agg_part_of<NK>(P, r, G.nparts) : -1;
         unsigned peers = __match_any_sync(0xffffffffu, p);  // one shared-memory atomic per distinct partition per warp
         int lane = threadIdx.x & 31;
         int leader = __ffs(peers) - 1;
@@ -759,7 +818,12 @@ static gsql_status agg_partition_batch(gsql_agg *a, StagedBatch *sb, int nparts,
     GSQL_CUDA(ctx, cudaMemsetAsync((char *)hist.p + nh * 8, 0, 8, ctx->stream));
     {
         KernelScope ks(ctx, "agg_part_hist");
-        k_agg_part_hist<<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>());
+        switch (a->nkeys) {  // the key count as a template argument keeps the key image in registers (see digest_of_keys)
+        case 1: k_agg_part_hist<1><<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>()); break;
+        case 2: k_agg_part_hist<2><<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>()); break;
+        case 3: k_agg_part_hist<3><<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>()); break;
+        default: k_agg_part_hist<0><<<nblocks, 256, (size_t)nparts * sizeof(unsigned int), ctx->stream>>>(P, G, hist.as<int64_t>()); break;
+        }
     }
     GSQL_CUDA(ctx, cudaGetLastError());
     size_t tb = 0;
@@ -778,7 +842,12 @@ static gsql_status agg_partition_batch(gsql_agg *a, StagedBatch *sb, int nparts,
     }
     {
         KernelScope ks(ctx, "agg_part_scatter");
-        k_agg_part_scatter<<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O);
+        switch (a->nkeys) {
+        case 1: k_agg_part_scatter<1><<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O); break;
+        case 2: k_agg_part_scatter<2><<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O); break;
+        case 3: k_agg_part_scatter<3><<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O); break;
+        default: k_agg_part_scatter<0><<<nblocks, 256, (size_t)nparts * sizeof(unsigned long long), ctx->stream>>>(P, G, offs.as<int64_t>(), O); break;
+        }
     }
     GSQL_CUDA(ctx, cudaGetLastError());
     for (int c = 0; c < sb->ncols; c++) {
@@ -928,7 +997,13 @@ extern "C" gsql_status gsql_agg_consume(gsql_agg *a, const gsql_batch *batch) {
             k_agg_smem<<<grid, AF_THREADS, a->fast.L.total, ctx->stream>>>(P, a->fast.L);
         } else {
             KernelScope ks(ctx, "agg_consume");
-            k_agg_consume<<<grid_rows(ctx, P.rows, 256, 8), 256, 0, ctx->stream>>>(P);
+            const int grid = grid_rows(ctx, P.rows, 256, 8);
+            switch (a->nkeys) {  // the key count as a template argument keeps the key image in registers (see digest_of_keys)
+            case 1: k_agg_consume<1><<<grid, 256, 0, ctx->stream>>>(P); break;
+            case 2: k_agg_consume<2><<<grid, 256, 0, ctx->stream>>>(P); break;
+            case 3: k_agg_consume<3><<<grid, 256, 0, ctx->stream>>>(P); break;
+            default: k_agg_consume<0><<<grid, 256, 0, ctx->stream>>>(P); break;
+            }
         }
         GSQL_CUDA(ctx, cudaGetLastError());
         unsigned long long h[C_COUNT];

@@ -17,19 +17,19 @@ ctx = api.Context(0)
 ctx.profile(True)
 peak, _ = bench.measured_peak_gbs()
 for case in which:
-    for v in ("GSQL_AGG_REG_NO_BULK", "GSQL_AGG_REG_PIPE", "GSQL_AGG_REG_STAGES", "GSQL_AGG_REG_SPREAD"):
+    for v in ("GSQL_AGG_REG_NO_BULK", "GSQL_AGG_REG_PIPE", "GSQL_AGG_REG_STAGES", "GSQL_AGG_PARTITION"):
         os.environ.pop(v, None)
     if case == "q1_nobulk":
         os.environ["GSQL_AGG_REG_NO_BULK"] = "1"
     if case == "q1_twobuf":
         os.environ["GSQL_AGG_REG_PIPE"] = "0"
-    if case == "q1_nospread":
-        os.environ["GSQL_AGG_REG_SPREAD"] = "0"
+    if case == "c5_nopart":
+        os.environ["GSQL_AGG_PARTITION"] = "0"
     if case == "q1_s3":
         os.environ["GSQL_AGG_REG_STAGES"] = "3"
     if case.startswith("q1"):
         e = bench.run_aux_agg(ctx, api, N, synth, dev, scale, peak)
-    elif case == "c5":
+    elif case.startswith("c5"):
         e = bench.run_aux_agg_c5(ctx, api, N, synth, dev, scale, peak)
     else:
         continue
