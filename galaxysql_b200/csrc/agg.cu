@@ -32,7 +32,15 @@ enum { C_NGROUPS = 0, C_OVERFLOW = 1, /* 2 = C_FALLBACK (agg_fast.cuh) */ C_FATA
 struct __align__(16) ASlot {
     unsigned long long digest;
     int gid;
-    int pad;
+    unsigned int hasmask;  // hint, bit a: "aggregate a's state of this group is known to be non-NULL" (has[gid] == 1); 0 is always safe
+};
+
+// What the probe learned besides the group id: the slot and the hint it carried.  With it the per-row work on the table
+// is one 16-byte slot read and the reductions — the separate reads of the group id and of every aggregate's `has` byte
+// (two of the four L2 transactions per row on the C5 share) only happen until the hint is set.
+struct SlotHint {
+    ASlot *sl;
+    unsigned int mask;
 };
 
 struct AggDev {  // device view of one aggregator's state
@@ -141,7 +149,7 @@ __device__ __forceinline__ unsigned long long load_group_key(const AggParams &P,
 // Finds or creates the group with key (kv, kn) / digest d.  Returns gid >= 0, or -1 when the table is full.
 template <int NK = 0>
 __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (&kv)[GSQL_MAX_KEYS], const bool (&kn)[GSQL_MAX_KEYS],
-                                             unsigned long long d, bool ignore_cap = false) {
+                                             unsigned long long d, bool ignore_cap = false, SlotHint *hint = nullptr) {
     if (NK == 0 && P.nkeys == 0) return 0;
     uint64_t s;
     bool dedicated = false;
@@ -155,17 +163,21 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
         // first look through the read-only path with an evict_last hint (the partition's slice of the table stays in L2 under the
         // evict-first input stream).  A stale EMPTY is harmless: the CAS below returns the real content; a digest never changes
         // once written, so a stale non-EMPTY value cannot exist.
-        unsigned long long cur = ld_keep_8(&sl->digest, l2_policy_evict_last());
+        // (one 16-byte read: digest, group id and hint; a stale id — still PENDING — is re-read below)
+        const int4 w = ld_keep_16(sl, l2_policy_evict_last());
+        unsigned long long cur = ((unsigned long long)(unsigned int)w.y << 32) | (unsigned int)w.x;
+        bool from_load = true;  // `cur` is what the read returned (not the result of a CAS that lost)
         bool mine = false;
         if (dedicated) {
             // dedicated slots are claimed through gid only: digest field carries a "claimed" mark
             unsigned long long prev = cur == DIGEST_EMPTY ? atomicCAS(&sl->digest, DIGEST_EMPTY, 1ULL) : cur;
             if (prev == DIGEST_EMPTY) mine = true;
+            else if (cur == DIGEST_EMPTY) from_load = false;
         } else if (cur == DIGEST_EMPTY) {
             if (!ignore_cap && *reinterpret_cast<volatile unsigned long long *>(&P.counters[C_NGROUPS]) >= (unsigned long long)P.gcap) return -1;
             unsigned long long prev = atomicCAS(&sl->digest, DIGEST_EMPTY, d);
             if (prev == DIGEST_EMPTY) mine = true;
-            else cur = prev;
+            else { cur = prev; from_load = false; }
         }
         if (mine) {  // first appearance: allocate the dense group id, publish keys, then the id
             // the lanes that create a group in the same step share ONE bump of the group counter (a first batch of millions
@@ -192,11 +204,16 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
             }
             __threadfence();
             *reinterpret_cast<volatile int *>(&sl->gid) = gid;
+            if (hint) { hint->sl = sl; hint->mask = 0; }
             return gid;
         }
         if (dedicated || cur == d) {
-            int gid;
-            while ((gid = *reinterpret_cast<volatile int *>(&sl->gid)) == GID_PENDING) __nanosleep(20);
+            int gid = from_load ? w.z : GID_PENDING;
+            while (gid == GID_PENDING) {
+                gid = *reinterpret_cast<volatile int *>(&sl->gid);
+                if (gid == GID_PENDING) __nanosleep(20);
+            }
+            if (hint) { hint->sl = sl; hint->mask = from_load ? (unsigned int)w.w : 0u; }
             if (P.exact) return gid;
             __threadfence();
             bool eq = true;
@@ -223,12 +240,12 @@ __device__ __forceinline__ int find_group_kv(const AggParams &P, const int64_t (
 }
 
 template <int NK = 0>
-__device__ __forceinline__ int find_group(const AggParams &P, int64_t r) {
+__device__ __forceinline__ int find_group(const AggParams &P, int64_t r, SlotHint *hint = nullptr) {
     if (NK == 0 && P.nkeys == 0) return 0;
     int64_t kv[GSQL_MAX_KEYS];
     bool kn[GSQL_MAX_KEYS];
     unsigned long long d = load_group_key<NK>(P, r, kv, kn);
-    return find_group_kv<NK>(P, kv, kn, d);
+    return find_group_kv<NK>(P, kv, kn, d, false, hint);
 }
 
 __device__ __forceinline__ int64_t in_i64(const DCol &c, int64_t r) {  // streaming (evict-first) reads: every input value is used once
@@ -278,7 +295,15 @@ __device__ __forceinline__ bool row_passes(const AggParams &P, int64_t r) {
     }
 }
 
-__device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, int gid, int64_t r) {
+// "This group's state of aggregate `aidx` is not NULL any more."  The slot's hint bit, once set, spares the row both the
+// read of has[gid] and the store; until then: a read that hits L2 instead of a one-byte store per row, and one RED.OR.
+__device__ __forceinline__ void mark_has(const AggDev &a, int gid, int aidx, SlotHint *h) {
+    if (h != nullptr && aidx >= 0 && ((h->mask >> aidx) & 1u)) return;
+    if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;
+    if (h != nullptr && h->sl != nullptr && aidx >= 0) atomicOr(&h->sl->hasmask, 1u << aidx);
+}
+
+__device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, int gid, int64_t r, int aidx = -1, SlotHint *h = nullptr) {
     if (a.filter_col >= 0) {  // AggOpenHashMap.java:114-131 — only Boolean / Long objects filter
         const DCol &f = P.in.c[a.filter_col];
         if (f.type == GSQL_T_INT64 && !in_null(f, r) && reinterpret_cast<const int64_t *>(f.data)[r] < 1) return;
@@ -307,12 +332,12 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
             long long carry = (sum < old ? 1 : 0) + (v < 0 ? -1 : 0);
             if (carry) atomicAdd(reinterpret_cast<unsigned long long *>(&a.hi[gid]), (unsigned long long)carry);
         }
-        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        mark_has(a, gid, aidx, h);
         return;
     case GSQL_AGG_AVG:
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), 1ULL);
-        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        mark_has(a, gid, aidx, h);
         return;
     case GSQL_AGG_SUM0:
         atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, c, r));
@@ -320,7 +345,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
     case GSQL_AGG_AVG_MERGE:  // (partial sum, partial count): the sum is NULL exactly when its count is 0
         atomicAdd(&a.d[gid], val_f64(P, c, r));
         if (!val_null(P, a.cols[1], r)) atomicAdd(reinterpret_cast<unsigned long long *>(&a.l[gid]), (unsigned long long)val_i64(P, a.cols[1], r));
-        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        mark_has(a, gid, aidx, h);
         return;
     case GSQL_AGG_MIN:
     case GSQL_AGG_MAX: {
@@ -328,7 +353,7 @@ __device__ __forceinline__ void accumulate(const AggParams &P, const AggDev &a, 
         long long v = a.in_type == GSQL_T_FP64 ? dbl_sortable(val_f64(P, c, r), mx) : val_i64(P, c, r);
         if (mx) atomicMax(reinterpret_cast<long long *>(&a.l[gid]), v);
         else atomicMin(reinterpret_cast<long long *>(&a.l[gid]), v);
-        if (!ld_keep_u8(&a.has[gid], l2_policy_evict_last())) a.has[gid] = 1;  // a read that hits L2 instead of a one-byte store per row
+        mark_has(a, gid, aidx, h);
         return;
     }
     default: return;
@@ -350,14 +375,15 @@ __global__ void __launch_bounds__(256) k_agg_consume(const __grid_constant__ Agg
         const int64_t r = live ? (P.row_list ? P.row_list[i] : P.row0 + i) : 0;
         const bool pass = live && row_passes(P, r);
         int gid = -1;
-        if (pass) gid = find_group<NK>(P, r);
+        SlotHint hint{nullptr, 0u};
+        if (pass) gid = find_group<NK>(P, r, &hint);
         __syncwarp();  // the aggregates' input loads below are issued by the whole warp again: coalesced
         if (pass) {
             if (gid < 0) {
                 unsigned long long o = atomicAdd(&P.counters[C_OVERFLOW], 1ULL);
                 P.overflow_rows[o] = r;
             } else {
-                for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r);
+                for (int a = 0; a < P.naggs; a++) accumulate(P, P.agg[a], gid, r, a, &hint);
             }
         }
         __syncwarp();  // ... and so are the key loads of the next row
