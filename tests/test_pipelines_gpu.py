@@ -58,6 +58,54 @@ def test_scan_filter_project_vs_numpy(gu, mem):
     assert ku.rows_multiset(got) == ku.rows_multiset(exp)
 
 
+@pytest.mark.parametrize("mem", ["host", "device"])
+@pytest.mark.parametrize("op", ["lt", "le", "gt", "ge", "eq", "ne", "none"])
+def test_scan_specialised_shape_vs_numpy_and_interpreter(gu, monkeypatch, mem, op):
+    """`column <cmp> constant` filters over INT / BIGINT columns with outputs that are columns or a * (1 - b) run on
+    k_scan_fast for NULL-free batches: bit-identical to numpy and to the bytecode kernel (GSQL_SCAN_NO_FAST=1), input order
+    kept inside a tile; a batch that carries a NULL buffer takes the bytecode kernel with the same handle."""
+    from galaxysql_b200 import api, native as N
+    E = api.E
+    n = 300_017
+    k32 = (ku.rand_u64(n, 11) % np.uint64(2557)).astype(np.int32) + 8035
+    k64 = (ku.rand_u64(n, 12) % np.uint64(1 << 40)).astype(np.int64) - (1 << 39)
+    price = ((ku.rand_u64(n, 13) % np.uint64(10_410_000)) + np.uint64(90_000)).astype(np.float64) / 100.0
+    disc = (ku.rand_u64(n, 14) % np.uint64(11)).astype(np.float64) / 100.0
+    cols = [(k32, None), (k64, None), (price, None), (disc, None)]
+    types = [N.T_INT32, N.T_INT64, N.T_FP64, N.T_FP64]
+    c = 9204
+    filt = {"lt": E.col(0) < c, "le": E.col(0) <= c, "gt": E.col(0) > c, "ge": E.col(0) >= c, "eq": E.col(0).eq(c), "ne": E.col(1).ne(int(k64[5])),
+            "none": None}[op]
+    keep = {"lt": k32 < c, "le": k32 <= c, "gt": k32 > c, "ge": k32 >= c, "eq": k32 == c, "ne": k64 != k64[5], "none": np.ones(n, bool)}[op]
+    outs = [E.col(1), E.col(2) * (1.0 - E.col(3)), E.col(0), E.col(3)]
+    exp = [k64[keep], (price * (1.0 - disc))[keep], k32[keep], disc[keep]]
+
+    def run(batch, nullable_out):
+        ctx = gu.ctx()
+        ctx.profile(True)
+        ctx.profile_reset()
+        s = api.Scan(ctx, types, outs, filter=filt)
+        got = gu.to_numpy(s.apply(gu.to_device(batch) if mem == "device" else batch, nullable_out=nullable_out))
+        s.close()
+        ctx.profile(False)
+        return got
+
+    fast = run(cols, False)
+    monkeypatch.setenv("GSQL_SCAN_NO_FAST", "1")
+    slow = run(cols, False)
+    monkeypatch.delenv("GSQL_SCAN_NO_FAST")
+    assert len(fast[0][0]) == int(keep.sum()) == len(slow[0][0])
+    # rows of one tile stay in input order, tiles land in cursor order: compare as multisets of whole rows, bit-exact
+    assert ku.rows_multiset(fast) == ku.rows_multiset([(e, None) for e in exp]) == ku.rows_multiset(slow)
+    if op == "none":  # no filter: every tile is full, so the output is the input in tile-permuted order; within a tile, in order
+        assert np.array_equal(np.sort(fast[0][0]), np.sort(k64))
+    # the same handle shape over a batch with a NULL buffer: the bytecode kernel, NULLs propagate through a * (1 - b)
+    pn = ku.with_nulls(price, 0.1, 15)
+    got = run([(k32, None), (k64, None), pn, (disc, None)], True)
+    expn = [(k64[keep], None), ((price * (1.0 - disc))[keep], pn[1][keep]), (k32[keep], None), (disc[keep], None)]
+    assert ku.rows_multiset(got) == ku.rows_multiset(expn)
+
+
 def test_scan_rejects_bad_programs_and_null_into_nonnull(gu):
     from galaxysql_b200 import api, native as N
     E = api.E
