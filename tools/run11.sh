@@ -12,12 +12,3 @@ for k in ("pipeline_q3","pipeline_c5"):
     e=d["roofline"].get(k,{}); print(k, e.get("ms_per_step"), e.get("rows_per_s"), e.get("parity",{}).get("match"))
 PY
 tail -3 gpurun_out/bench_n1.err
-for WL in q3 c5; do
-timeout 600 python bench.py --workload $WL --steps 3 --warmup 3 > gpurun_out/bench_${WL}_n1.json 2> gpurun_out/bench_${WL}_n1.err; python - <<PY
-import json
-d=json.loads(open("gpurun_out/bench_${WL}_n1.json").read().strip().splitlines()[-1])
-print("$WL ms", d["ms_per_step"], "value", d["value"]/1e9, d["parity"]["match"])
-print({a:round(b,3) for a,b in d["roofline"]["per_kernel_ms_per_step"].items()})
-PY
-tail -2 gpurun_out/bench_${WL}_n1.err
-done
