@@ -98,6 +98,15 @@ public final class GpuNative {
 
     public static native void scanDestroy(long scan);
 
+    /**
+     * PagesSerde wire format (gsql_serde_serialize): the staging batch as a stream of framed pages of at most pageRows rows
+     * each — int32 positionCount | int8 marker (0 = UNCOMPRESSED) | int32 uncompressedSize | int32 sizeInBytes | raw page.
+     */
+    public static native byte[] serdeSerialize(long ctx, long staging, int pageRows);
+
+    /** Decodes every framed page in pages[offset, offset + length) into outStaging (grown as needed); returns the rows. */
+    public static native int serdeDeserialize(long ctx, byte[] pages, int offset, int length, long outStaging);
+
     // ---- local hash-partition exchange (gsql_xchg_partition)
     public static native long xchgCreate(long ctx, int[] types, int[] channels, int[] keyTypes, int nparts, int mode);
 

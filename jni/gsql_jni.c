@@ -491,6 +491,48 @@ NATIVE(void, scanDestroy)(JNIEnv *env, jclass c, jlong sh) {
 }
 
 /* ---- local hash-partition exchange -------------------------------------------------------------------------- */
+/* ---- PagesSerde wire format (gsql_serde_*): a staging batch <-> the framed page stream of PagesSerdeUtil.writeSerializedChunk */
+NATIVE(jbyteArray, serdeSerialize)(JNIEnv *env, jclass c, jlong ctx, jlong sh, jint pageRows) {
+    staging *in = (staging *)(intptr_t)sh;
+    gsql_ctx *cx = (gsql_ctx *)(intptr_t)ctx;
+    int64_t need = 0, got = 0;
+    int st = gsql_serde_size(cx, as_batch(in, 0), pageRows, &need);
+    if (st != GSQL_OK) { throw_status(env, cx, st); return NULL; }
+    if (need > 0x7fffffff) { throw_status(env, NULL, GSQL_E_CAPACITY); return NULL; } /* a Java byte[] holds 2^31 - 1 bytes */
+    void *buf = NULL;
+    if (gsql_host_alloc((size_t)(need ? need : 1), &buf) != GSQL_OK) { throw_status(env, NULL, GSQL_E_OOM); return NULL; }
+    st = gsql_serde_serialize(cx, as_batch(in, 0), pageRows, buf, need, &got);
+    jbyteArray out = NULL;
+    if (st != GSQL_OK) {
+        throw_status(env, cx, st);
+    } else {
+        out = (*env)->NewByteArray(env, (jsize)got);
+        if (out) (*env)->SetByteArrayRegion(env, out, 0, (jsize)got, (const jbyte *)buf);
+    }
+    gsql_host_free(buf);
+    return out;
+}
+
+NATIVE(jint, serdeDeserialize)(JNIEnv *env, jclass c, jlong ctx, jbyteArray pages, jint offset, jint length, jlong oh) {
+    staging *o = (staging *)(intptr_t)oh;
+    gsql_ctx *cx = (gsql_ctx *)(intptr_t)ctx;
+    if (!pages || offset < 0 || length < 0 || offset + (int64_t)length > (*env)->GetArrayLength(env, pages)) { throw_status(env, NULL, GSQL_E_INVALID); return -1; }
+    void *buf = NULL;
+    if (gsql_host_alloc((size_t)(length ? length : 1), &buf) != GSQL_OK) { throw_status(env, NULL, GSQL_E_OOM); return -1; }
+    (*env)->GetByteArrayRegion(env, pages, offset, length, (jbyte *)buf);
+    int64_t rows = 0;
+    /* first call learns the row count when the staging batch is too small (GSQL_E_CAPACITY reports the need) */
+    int st = gsql_serde_deserialize(cx, buf, length, GSQL_MEM_HOST, as_batch(o, 1), o->cap, &rows);
+    if (st == GSQL_E_CAPACITY && rows > o->cap) {
+        if (staging_reserve(o, rows)) { gsql_host_free(buf); throw_status(env, NULL, GSQL_E_OOM); return -1; }
+        st = gsql_serde_deserialize(cx, buf, length, GSQL_MEM_HOST, as_batch(o, 1), o->cap, &rows);
+    }
+    gsql_host_free(buf);
+    if (st != GSQL_OK) { throw_status(env, cx, st); return -1; }
+    staging_filled(o, rows);
+    return (jint)rows;
+}
+
 NATIVE(jlong, xchgCreate)(JNIEnv *env, jclass c, jlong ctx, jintArray types, jintArray channels, jintArray keyTypes, jint nparts, jint mode) {
     gsql_xchg_spec s;
     int32_t n;

@@ -10,6 +10,7 @@
 typedef int32_t jint;
 typedef int64_t jlong;
 typedef uint8_t jboolean;
+typedef int8_t jbyte;
 typedef double jdouble;
 typedef jint jsize;
 typedef void *jobject;
@@ -20,6 +21,7 @@ typedef jarray jintArray;
 typedef jarray jlongArray;
 typedef jarray jdoubleArray;
 typedef jarray jbooleanArray;
+typedef jarray jbyteArray;
 typedef jobject jthrowable;
 
 #define JNI_ABORT 2
@@ -48,6 +50,9 @@ struct JNINativeInterface_ {
     jlongArray (*NewLongArray)(JNIEnv *env, jsize len);
     jdoubleArray (*NewDoubleArray)(JNIEnv *env, jsize len);
     jbooleanArray (*NewBooleanArray)(JNIEnv *env, jsize len);
+    jbyteArray (*NewByteArray)(JNIEnv *env, jsize len);
+    void (*SetByteArrayRegion)(JNIEnv *env, jbyteArray array, jsize start, jsize len, const jbyte *buf);
+    void (*GetByteArrayRegion)(JNIEnv *env, jbyteArray array, jsize start, jsize len, jbyte *buf);
     void *(*GetPrimitiveArrayCritical)(JNIEnv *env, jarray array, jboolean *isCopy);
     void (*ReleasePrimitiveArrayCritical)(JNIEnv *env, jarray array, void *carray, jint mode);
 };

@@ -114,3 +114,57 @@ def test_reference_types_the_java_side_imports_exist_where_cited():
         pkg = ".".join(cls.split(".")[:-1])
         assert re.search(r"extends\s+" + simple + r"\b", src), f"{rel} must extend {simple}"
         assert f"package {pkg};" in src or f"import {cls};" in src, f"{rel}: {simple} must be visible (same package or imported)"
+
+
+def _header_enum_values():
+    """name -> value of every `NAME = <int>` enumerator / `#define NAME <int>` in include/gsql_gpu.h."""
+    src = _strip_comments(open(os.path.join(ROOT, "include", "gsql_gpu.h")).read())
+    out = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(GSQL_[A-Z0-9_]+)\s*=\s*(-?\d+)", src)}
+    out.update({m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(GSQL_[A-Z0-9_]+)\s+(\d+)\b", src)})
+    return out
+
+
+def test_java_constants_mirror_the_header():
+    """The Java side restates a few enumerations of include/gsql_gpu.h as int constants (no generated binding in an image
+    without a JDK): type codes, aggregate kinds, expression opcodes, the instruction limit.  They must stay equal."""
+    h = _header_enum_values()
+    files = _java_files()
+
+    def consts(rel):
+        src = _strip_comments(files[os.path.join(JAVA, PKG, rel)])
+        out = {}
+        for decl in re.findall(r"public static final int\s+([^;]+);", src, flags=re.S):
+            for name, val in re.findall(r"(\w+)\s*=\s*(-?\d+)", decl):
+                out[name] = int(val)
+        return out
+
+    native = consts("operator/gpu/GpuNative.java")
+    for name in ("T_INT32", "T_INT64", "T_FP64", "T_DEC128"):
+        assert native[name] == h["GSQL_" + name], name
+    agg = consts("operator/gpu/GpuAggSpec.java")
+    for name in ("COUNT_STAR", "COUNT", "SUM", "AVG", "MIN", "MAX", "SUM0"):
+        assert agg[name] == h["GSQL_AGG_" + name], name
+    expr = consts("operator/gpu/GpuExpression.java")
+    ops = {k: v for k, v in expr.items() if k.startswith("OP_")}
+    assert len(ops) >= 19
+    for name, val in ops.items():
+        assert val == h["GSQL_" + name], name
+    assert expr["MAX_INSTRUCTIONS"] == h["GSQL_MAX_EXPR_INS"]
+    # every opcode of the header that a program may contain has its Java constant
+    assert {k[len("GSQL_"):] for k in h if k.startswith("GSQL_OP_")} == set(ops)
+
+
+def test_pages_serde_frame_layout_matches_the_codec():
+    """GpuPagesSerde splits / builds the 13-byte page frame by hand; the offsets must be the oracle codec's
+    (oracle/serde.py restates PagesSerdeUtil.writeSerializedChunk): int32 positionCount | int8 marker | int32 uncompressedSize |
+    int32 sizeInBytes, little-endian."""
+    import numpy as np
+    from oracle import serde
+    cols = [(np.arange(5, dtype=np.int64), None), (np.arange(5, dtype=np.float64), np.array([0, 1, 0, 0, 1], bool))]
+    blob = serde.serialize(cols, [1, 2], 5)
+    pos, marker, unc, size = int.from_bytes(blob[0:4], "little"), blob[4], int.from_bytes(blob[5:9], "little"), int.from_bytes(blob[9:13], "little")
+    assert (pos, marker) == (5, 0) and unc == size == len(blob) - 13
+    src = _strip_comments(open(os.path.join(JAVA, PKG, "mpp/execution/buffer/GpuPagesSerde.java")).read())
+    assert "FRAME_BYTES = 4 + 1 + 4 + 4" in src
+    for needle in ("all.getInt(at)", "all.getInt(at + 5)", "all.getInt(at + 9)", "f.setInt(0,", "f.setByte(4, 0)", "f.setInt(5,", "f.setInt(9,"):
+        assert needle in src, needle
