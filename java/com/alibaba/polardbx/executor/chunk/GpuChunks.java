@@ -1,5 +1,6 @@
 package com.alibaba.polardbx.executor.chunk;
 
+import com.alibaba.polardbx.common.utils.timezone.InternalTimeZone;
 import com.alibaba.polardbx.executor.operator.gpu.GpuExecutorException;
 import com.alibaba.polardbx.executor.operator.gpu.GpuNative;
 import com.alibaba.polardbx.executor.operator.gpu.GpuTypes;
@@ -43,6 +44,10 @@ public final class GpuChunks {
                 arrays[c] = ((LongBlock) b).longArray();
             } else if (b instanceof DoubleBlock) {
                 arrays[c] = ((DoubleBlock) b).doubleArray();
+            } else if (b instanceof TimestampBlock) {
+                arrays[c] = ((TimestampBlock) b).getPacked(); // DATETIME / TIMESTAMP: MySQL packed longs, a BIGINT column to the GPU
+            } else if (b instanceof DateBlock && ((DateBlock) b).getSelection() == null) {
+                arrays[c] = ((DateBlock) b).getPacked();
             } else {
                 direct = false;
             }
@@ -108,6 +113,10 @@ public final class GpuChunks {
                 int at = selection != null ? selection[i] : offset + i;
                 if (b.isNull(i)) {
                     (nl == null ? nl = new boolean[span] : nl)[at] = true;
+                } else if (b instanceof DateBlock) {
+                    v[at] = ((DateBlock) b).getPackedLong(i); // (honours the block's own selection)
+                } else if (b instanceof TimestampBlock) {
+                    v[at] = ((TimestampBlock) b).getPackedLong(i);
                 } else {
                     v[at] = b.getLong(i);
                 }
@@ -118,7 +127,7 @@ public final class GpuChunks {
         nulls[c] = nl;
     }
 
-    /** Rows [from, from+rows) of a staging batch as a fresh Chunk of IntegerBlock / LongBlock / DoubleBlock. */
+    /** Rows [from, from+rows) of a staging batch as a fresh Chunk of IntegerBlock / LongBlock / DoubleBlock / DateBlock / TimestampBlock. */
     public static Chunk toChunk(long staging, List<DataType> types, int from, int rows) {
         Block[] blocks = new Block[types.size()];
         for (int c = 0; c < blocks.length; c++) {
@@ -128,9 +137,18 @@ public final class GpuChunks {
             case GpuNative.T_INT32:
                 blocks[c] = new IntegerBlock(0, rows, nulls, (int[]) values);
                 break;
-            case GpuNative.T_INT64:
-                blocks[c] = new LongBlock(0, rows, nulls, (long[]) values);
+            case GpuNative.T_INT64: {
+                DataType type = types.get(c);
+                Class<?> clazz = type.getDataClass();
+                if (clazz == java.sql.Date.class) { // as DateBlockBuilder.build():146-149 / TimestampBlockBuilder.build()
+                    blocks[c] = new DateBlock(0, rows, nulls, (long[]) values, type, InternalTimeZone.DEFAULT_TIME_ZONE);
+                } else if (clazz == java.sql.Timestamp.class) {
+                    blocks[c] = new TimestampBlock(0, rows, nulls, (long[]) values, type, InternalTimeZone.DEFAULT_TIME_ZONE);
+                } else {
+                    blocks[c] = new LongBlock(0, rows, nulls, (long[]) values);
+                }
                 break;
+            }
             case GpuNative.T_FP64:
                 blocks[c] = new DoubleBlock(0, rows, nulls, (double[]) values);
                 break;

@@ -84,6 +84,10 @@ public final class GpuExpression {
      * literals, + - * / unary minus, the six comparisons, AND / OR / NOT, IS NULL / IS NOT NULL, CAST to BIGINT / DOUBLE.
      */
     public static GpuExpression fromRex(RexNode node, List<DataType> inputTypes) {
+        if (node instanceof RexInputRef) { // a bare column passes through whatever its block type (DATE / DATETIME as packed longs)
+            int i = ((RexInputRef) node).getIndex();
+            return i < inputTypes.size() && GpuTypes.code(inputTypes.get(i)) >= 0 ? col(i) : null;
+        }
         GpuExpression e = translate(node, inputTypes);
         return e != null && e.fits() ? e : null;
     }
@@ -91,7 +95,7 @@ public final class GpuExpression {
     private static GpuExpression translate(RexNode node, List<DataType> inputTypes) {
         if (node instanceof RexInputRef) {
             int i = ((RexInputRef) node).getIndex();
-            return i < inputTypes.size() && GpuTypes.code(inputTypes.get(i)) >= 0 ? col(i) : null;
+            return i < inputTypes.size() && GpuTypes.isNumeric(inputTypes.get(i)) ? col(i) : null; // inside an expression: numbers only
         }
         if (node instanceof RexLiteral) {
             Object v = ((RexLiteral) node).getValue3();

@@ -23,7 +23,29 @@ public final class GpuTypes {
         if (DataTypeUtil.equalsSemantically(type, DataTypes.DoubleType)) {
             return GpuNative.T_FP64; // DoubleBlock
         }
+        if (isPackedTime(type)) {
+            return GpuNative.T_INT64; // DateBlock / TimestampBlock: long[] packed
+        }
         return -1;
+    }
+
+    /**
+     * DATE and DATETIME / TIMESTAMP columns: DateBlock and TimestampBlock hold one MySQL packed long per row
+     * (chunk/DateBlock.java:43, chunk/TimestampBlock.java:47; BlockBuilders.java:73-76 picks them by data class), hash it
+     * with Long.hashCode like LongBlock (DateBlock.java:138-142, TimestampBlock.java:105-109) and compare rows by that long
+     * (DateBlock.java:174-191).  On the GPU such a column IS a BIGINT column: join keys, group keys, exchange partitioning
+     * and pass-through are bit-identical; GpuChunks rebuilds the Block class from the DataType on the way back.
+     * Arithmetic and comparisons with literals are NOT served (a literal would have to be packed the same way):
+     * GpuExpression only lets such a column through as a bare input reference.
+     */
+    public static boolean isPackedTime(DataType type) {
+        Class<?> clazz = type.getDataClass();
+        return clazz == java.sql.Date.class || clazz == java.sql.Timestamp.class;
+    }
+
+    /** INT / BIGINT / DOUBLE: the types expressions may compute with. */
+    public static boolean isNumeric(DataType type) {
+        return code(type) >= 0 && !isPackedTime(type);
     }
 
     public static boolean supported(List<DataType> types) {
