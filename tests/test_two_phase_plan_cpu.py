@@ -84,3 +84,16 @@ def test_partial_then_final_equals_single_phase_on_the_oracle():
     # a group lives on exactly one rank after the repartition: the union of the ranks' results is the single-phase result
     assert len(got[0][0]) == len(single[0][0])
     assert ku.rows_multiset(got) == ku.rows_multiset(single)
+
+
+def test_q3_scan_programs_have_the_shape_the_specialised_kernel_recognises():
+    """scan.cu's scan_fast_plan matches `COL c, CONST_I64 k, <cmp>` filters and `COL` / `COL a, CONST_F64 1.0, COL b, SUB, MUL`
+    outputs.  The Q3 pipeline builds its programs with api.E: if the builder ever emitted another instruction order the
+    pipeline would silently fall back to the bytecode kernel (2.3x slower scans) — pin the sequences here."""
+    from galaxysql_b200 import api
+    E = api.E
+    assert (E.col(1) * (1.0 - E.col(2))).ins == [(N.OP_COL, 1, 0), (N.OP_CONST_F64, 0, 1.0), (N.OP_COL, 2, 0), (N.OP_SUB, 0, 0), (N.OP_MUL, 0, 0)]
+    assert (E.col(3) > pipelines.Q3_DATE).ins == [(N.OP_COL, 3, 0), (N.OP_CONST_I64, 0, pipelines.Q3_DATE), (N.OP_GT, 0, 0)]
+    assert (E.col(2) < pipelines.Q3_DATE).ins == [(N.OP_COL, 2, 0), (N.OP_CONST_I64, 0, pipelines.Q3_DATE), (N.OP_LT, 0, 0)]
+    assert E.col(1).eq(pipelines.Q3_SEGMENT).ins == [(N.OP_COL, 1, 0), (N.OP_CONST_I64, 0, pipelines.Q3_SEGMENT), (N.OP_EQ, 0, 0)]
+    assert E.col(0).ins == [(N.OP_COL, 0, 0)]
